@@ -1,0 +1,154 @@
+/* include/tbirch.h -- C ABI of libtbirch.so, the B200 (sm_100a) implementation of
+ * ternary-birch's p-neighbor Hecke hot path.
+ *
+ * This is the drop-in boundary: plain C, POD arguments, no torch / C++ types.
+ * Each entry point names the reference interface it stands in for (paths are
+ * relative to the reference's src/).  The C++ facade in
+ * ternary_birch_b200/host/ re-creates the reference's class API
+ * (Genus<R>::hecke_matrix_sparse, ...) on top of these calls, and INTEGRATION.md
+ * shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - Every function returning int returns a tb_status.  On failure the
+ *     calling thread's tb_last_error() holds the SAME what() string the
+ *     reference's C++ exception carries, and tb_status says which exception
+ *     type the facade must rethrow.
+ *   - `precise` = 0: int64 wrap-around arithmetic (the reference's Genus<Z64>,
+ *     pyx precise=False).  `precise` = 1: overflow-checked 128-bit arithmetic
+ *     replacing GMP (the reference's Genus<Z>, pyx precise=True); an operation
+ *     that would exceed 127 bits reports TB_ERR_OVERFLOW.
+ *   - There is no CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with TB_ERR_RUNTIME.
+ *   - Destination pointers of the tb_*_copy_* calls may be host OR device
+ *     memory (unified virtual addressing decides).
+ *   - A tb_genus and the objects made from it must be used by one host thread
+ *     at a time (the reference's Genus has the same restriction).
+ */
+#ifndef TBIRCH_H
+#define TBIRCH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TBIRCH_ABI_VERSION 1
+
+typedef enum tb_status {
+    TB_OK = 0,
+    TB_ERR_INVALID_ARGUMENT = 1,  /* std::invalid_argument: "Prime must not divide the discriminant." (Genus.h:336,345), "Key not found." (HashMap.h:77), "Invalid conductor." / "Eigenvector has incorrect dimension." (Genus.h:367,373) */
+    TB_ERR_OVERFLOW = 2,          /* std::overflow_error: NeighborManager.h:350-352 */
+    TB_ERR_DOMAIN = 3,            /* std::domain_error: "No more isometries." (IsometrySequence.h:52), "Must have 63 or fewer prime divisors." (Genus.h:59) */
+    TB_ERR_RUNTIME = 4            /* std::runtime_error: CUDA failures, missing device, unsupported sizes */
+} tb_status;
+
+typedef struct tb_genus tb_genus;
+typedef struct tb_hecke tb_hecke;
+typedef struct tb_isoseq tb_isoseq;
+
+/* The state Genus<R> keeps after construction (Genus.h:423-434; GenusRep,
+ * Genus.h:12-26), flattened.  All arrays are host memory, copied by
+ * tb_genus_create; the caller may free them afterwards. */
+typedef struct tb_genus_desc {
+    int64_t N;                  /* number of genus representatives (Genus::size) */
+    int64_t K;                  /* number of prime divisors; 2^K conductors */
+    uint64_t seed;              /* Genus::seed_ (orders the isotropic lines, Fp.h:12-15) */
+    int64_t disc;               /* Genus::disc */
+    const int64_t *primes;      /* [K]      Genus::prime_divisors */
+    const int64_t *conductors;  /* [2^K]    Genus::conductors */
+    const int64_t *dims;        /* [2^K]    Genus::dims */
+    const int64_t *q;           /* [N][6]   GenusRep::q = (a,b,c,f,g,h) */
+    const int64_t *s;           /* [N][9]   GenusRep::s    (row-major a11..a33) */
+    const int64_t *sinv;        /* [N][9]   GenusRep::sinv */
+    const int64_t *scalar;      /* [N]      birch_util::my_pow(GenusRep::es) */
+    const int32_t *lut;         /* [2^K][N] Genus::lut_positions */
+} tb_genus_desc;
+
+/* ---- library ---------------------------------------------------------- */
+int tb_abi_version(void);
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char *tb_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py's
+ * "gpu_launches" claim). */
+uint64_t tb_launch_count(void);
+/* Device time in ms of the last neighbor-kernel launch sequence of `g`
+ * (CUDA events on g's stream), and the number of neighbors it covered. */
+int tb_last_kernel_time(tb_genus *g, float *ms_neighbors, float *ms_rows, int64_t *neighbors);
+
+/* ---- genus table ------------------------------------------------------ */
+/* Replaces the state built by Genus<R>::Genus (Genus.h:37-246) and copied by the
+ * converting constructor Genus<Z64>(const Genus<Z>&) (Genus.h:248-303): uploads
+ * the table, builds the device hash table of representatives
+ * (HashMap.h:107-147, keyed by QuadForm::hash_value, QuadForm.cpp:779-803). */
+int tb_genus_create(const tb_genus_desc *desc, tb_genus **out);
+void tb_genus_destroy(tb_genus *g);
+/* Run all of g's work on this cudaStream_t (default: the legacy default stream). */
+int tb_genus_set_stream(tb_genus *g, void *cuda_stream);
+/* Re-upload the table into the existing device buffers (same N, K). */
+int tb_genus_upload(tb_genus *g, const tb_genus_desc *desc);
+int64_t tb_genus_size(const tb_genus *g);            /* Genus::size, Genus.h:306 */
+int64_t tb_genus_num_conductors(const tb_genus *g);
+int64_t tb_genus_conductor(const tb_genus *g, int64_t k);
+int64_t tb_genus_dim(const tb_genus *g, int64_t k);  /* Genus::dimension_map, Genus.h:321-330 */
+
+/* ---- Hecke matrices --------------------------------------------------- */
+/* Genus<R>::hecke_matrix_sparse / hecke_matrix_dense (Genus.h:332-348) and the
+ * loops behind them (533-672, 674-848): T_p for ALL 2^K conductors in one pass.
+ * The matrices stay on the device inside *out until copied. `rep_begin/rep_end`
+ * restrict the pass to rows of representatives [rep_begin, rep_end) -- the
+ * multi-GPU shard; pass 0, N for the whole matrix. */
+int tb_hecke_compute(tb_genus *g, uint64_t p, int precise, tb_hecke **out);
+int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise,
+                          int64_t rep_begin, int64_t rep_end, tb_hecke **out);
+int64_t tb_hecke_num_conductors(const tb_hecke *h);
+int64_t tb_hecke_conductor(const tb_hecke *h, int64_t k);
+int64_t tb_hecke_dim(const tb_hecke *h, int64_t k);   /* columns; full rows of T^(k) */
+int64_t tb_hecke_rows(const tb_hecke *h, int64_t k);  /* rows present in this shard */
+int64_t tb_hecke_row_begin(const tb_hecke *h, int64_t k);
+int64_t tb_hecke_nnz(const tb_hecke *h, int64_t k);
+/* CSR triple in the reference's order (data, indices, indptr), Genus.h:662-671:
+ * data[nnz], indices[nnz], indptr[rows+1]. */
+int tb_hecke_copy_sparse(tb_hecke *h, int64_t k, int32_t *data, int32_t *indices, int32_t *indptr);
+/* Row-major rows x dim block, Genus.h:811-846. */
+int tb_hecke_copy_dense(tb_hecke *h, int64_t k, int32_t *matrix);
+void tb_hecke_destroy(tb_hecke *h);
+
+/* ---- eigenvalues ------------------------------------------------------ */
+/* Genus<R>::eigenvalues (Genus.h:392-421) / _eigenvectors (446-514).
+ *   vecs[V][N]   eigenvectors lifted to the full genus (Genus::eigenvector, 350-390)
+ *   cond_mask[V] conductor index k of each vector (Eigenvector::conductor_index)
+ *   rep_index[V] representative each vector is evaluated at
+ *                (EigenvectorManager::finalize, Eigenvector.h:170-185)
+ *   out[V]       the eigenvalues, in vector order. */
+int tb_eigenvalues(tb_genus *g, uint64_t p, int precise, int64_t V, const int32_t *vecs,
+                   const int64_t *cond_mask, const int64_t *rep_index, int32_t *out);
+
+/* ---- isometry sequence ------------------------------------------------ */
+/* IsometrySequence<R,S,T> (IsometrySequence.h:19-92): rep-major, t-minor stream
+ * of (isometry, denominator, src, dst).  tb_isoseq_next past the end fails with
+ * TB_ERR_DOMAIN "No more isometries.". */
+int tb_isoseq_open(tb_genus *g, uint64_t p, int precise, tb_isoseq **out);
+int tb_isoseq_done(const tb_isoseq *it);
+int tb_isoseq_next(tb_isoseq *it, int64_t isometry[9], int64_t *denominator, int64_t *src, int64_t *dst);
+/* Bulk form: up to max_records records of 12 int64 (isometry[9], denominator,
+ * src, dst); returns the count through *got. */
+int tb_isoseq_read(tb_isoseq *it, int64_t max_records, int64_t *records, int64_t *got);
+void tb_isoseq_close(tb_isoseq *it);
+
+/* ---- per-neighbor records (parity tests) ------------------------------ */
+/* The loop body of Genus.h:567-618 for every (n, t) with n in
+ * [rep_begin, rep_end): 20 int64 per neighbor = isotropic vector[3], reduced
+ * form[6], isometry rep -> neighbor[9], r, spin.  `records` is host or device. */
+int tb_neighbor_records(tb_genus *g, uint64_t p, int precise, int64_t rep_begin, int64_t rep_end,
+                        int64_t *records);
+
+/* ---- integer-pipe microbenchmark -------------------------------------- */
+/* Measures the int32 issue peak used as the roofline denominator: runs an
+ * unrolled IMAD + IADD3/LOP3 chain on every SM.  Returns int32 op/s. */
+int tb_int_peak(double *imad_ops_per_s, double *iadd_ops_per_s, double *mixed_ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TBIRCH_H */

@@ -1,0 +1,438 @@
+// tb_kernels.cuh -- the CUDA kernels of the p-neighbor Hecke path (sm_100a).
+//
+//   inverse_lut_kernel   Fp::make_inverse_lut                      Fp.h:228-269
+//   prep_reps_kernel     NeighborManager ctor constants            NeighborManager.h:13-48
+//   neighbors_kernel     the (rep, t) loop body                    Genus.h:562-618
+//   rows_kernel          per-conductor row accumulation + CSR      Genus.h:620-657
+//   indptr_scan_kernel   CSR row pointers                          Genus.h:656
+//   dense_scatter_kernel dense rows                                Genus.h:785-803
+//   eigen_dot_kernel     eigenvalue accumulation                   Genus.h:490-499
+//
+// The path is integer-issue bound with an L2-resident working set; no tensor
+// cores, no TMA (there is no bulk tile to move: every thread's operands live
+// in registers and the genus table is a few MB of random 128-byte lines).
+#pragma once
+
+#include "tb_neighbor.cuh"
+
+namespace tb {
+
+#define TB_NBR_THREADS 128
+
+// ---------------------------------------------------------------------------
+// Inverse table mod p (one launch per prime).
+// ---------------------------------------------------------------------------
+__global__ void inverse_lut_kernel(PrimeCtx pc, u32 *lut)
+{
+    u32 a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= pc.p) return;
+    PrimeCtx local = pc;
+    local.use_lut = 0;
+    lut[a] = a ? fp_pow(a, pc.p - 2u, local) : 0u;
+}
+
+// ---------------------------------------------------------------------------
+// Per-representative constants for this prime.  base[n] = (x0, y0, z0) comes
+// from the host (it consumes the reference's sequential RNG stream).
+// ---------------------------------------------------------------------------
+__global__ void prep_reps_kernel(GenusCtx gc, PrimeCtx pc, const u32 *base, int rep_begin, int rows, RepPrime *out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const int n = rep_begin + i;
+    const i64 *cur = gc.cur + (size_t)n * TB_REC_WORDS;
+    const u32 p = pc.p;
+    RepPrime rp;
+    rp.pad = 0;
+    if (p == 2u)
+    {
+        rp.a = rp.b = rp.h = 0;
+        rp.x0 = base[3 * i + 0]; rp.y0 = base[3 * i + 1]; rp.a0 = base[3 * i + 2];
+        rp.delta = 0;
+        out[i] = rp;
+        return;
+    }
+    const u32 a = fp_mod_i64(cur[0], pc), b = fp_mod_i64(cur[1], pc);
+    const u32 f = fp_mod_i64(cur[3], pc), g = fp_mod_i64(cur[4], pc), h = fp_mod_i64(cur[5], pc);
+    const u32 x0 = base[3 * i + 0], y0 = base[3 * i + 1];
+    // a0 = a - 2 a x0 - g - h y0 ; delta = b - 2 b y0 - f + h - h x0      NeighborManager.h:34-47
+    u32 t = fp_mul(a, x0, pc);
+    u32 a0 = fp_sub(fp_sub(fp_sub(a, fp_add(t, t, p), p), g, p), fp_mul(h, y0, pc), p);
+    t = fp_mul(b, y0, pc);
+    u32 delta = fp_sub(fp_add(fp_sub(fp_sub(b, fp_add(t, t, p), p), f, p), h, p), fp_mul(h, x0, pc), p);
+    rp.a = a; rp.b = b; rp.h = h; rp.x0 = x0; rp.y0 = y0; rp.a0 = a0; rp.delta = delta;
+    out[i] = rp;
+}
+
+// ---------------------------------------------------------------------------
+// neighbors_kernel: one thread per (representative, t).
+//   MODE_PACKED   W[i] = (r << K) | spin                         Genus.h:617
+//   MODE_RECORDS  20 int64: line[3], reduced form[6], isometry[9], r, spin
+//   MODE_ISOSEQ   12 int64: composed isometry[9], denominator, src, dst
+// err[0] / err[1]: smallest neighbor index that overflowed / missed the table.
+// ---------------------------------------------------------------------------
+enum { MODE_PACKED = 0, MODE_RECORDS = 1, MODE_ISOSEQ = 2 };
+
+struct NbrLaunch {
+    int rep_begin;
+    int rows;
+    u32 P1;           // p + 1
+    u32 pad;
+    u64 total;        // rows * P1
+    InvDiv dP1;
+    const RepPrime *rp;
+    u32 *W;
+    i64 *records;
+    u64 *err;
+};
+
+template <class Z, int MODE>
+__global__ void __launch_bounds__(TB_NBR_THREADS)
+neighbors_kernel(const __grid_constant__ GenusCtx gc, const __grid_constant__ PrimeCtx pc,
+                 const __grid_constant__ NbrLaunch L)
+{
+    if (threadIdx.x == 0) *cta_flag_ptr() = 0u;
+    __syncthreads();
+
+    const u64 i = (u64)blockIdx.x * TB_NBR_THREADS + threadIdx.x;
+    if (i < L.total)
+    {
+        u64 t64;
+        const u64 row = udivmod(i, L.dP1, t64);
+        const u32 t = (u32)t64;
+        const int n = L.rep_begin + (int)row;
+        const RepPrime rp = L.rp[row];
+
+        Neighbor<Z> o;
+        const int status = one_neighbor<Z>(n, t, rp, pc, gc, MODE == MODE_ISOSEQ, o);
+        if (status == NBR_OVERFLOW) atomicMin(L.err + 0, i);
+        else if (status == NBR_NOT_FOUND) atomicMin(L.err + 1, i);
+
+        if (MODE == MODE_PACKED)
+        {
+            L.W[i] = status == NBR_OK ? (((u32)o.r << gc.K) | o.spin) : 0xffffffffu;
+        }
+        else if (MODE == MODE_RECORDS)
+        {
+            i64 *out = L.records + i * 20;
+            out[0] = o.vx; out[1] = o.vy; out[2] = o.vz;
+            if (status == NBR_OK)
+            {
+                out[3] = o.q.a.low64(); out[4] = o.q.b.low64(); out[5] = o.q.c.low64();
+                out[6] = o.q.f.low64(); out[7] = o.q.g.low64(); out[8] = o.q.h.low64();
+                out[9] = o.s.a11.low64(); out[10] = o.s.a12.low64(); out[11] = o.s.a13.low64();
+                out[12] = o.s.a21.low64(); out[13] = o.s.a22.low64(); out[14] = o.s.a23.low64();
+                out[15] = o.s.a31.low64(); out[16] = o.s.a32.low64(); out[17] = o.s.a33.low64();
+                out[18] = o.r; out[19] = o.spin;
+            }
+        }
+        else
+        {
+            i64 *out = L.records + i * 12;
+            if (status == NBR_OK)
+            {
+                const Iso<Z> &c = o.comp;
+                if (!(c.a11.fits_i64() && c.a12.fits_i64() && c.a13.fits_i64() && c.a21.fits_i64() &&
+                      c.a22.fits_i64() && c.a23.fits_i64() && c.a31.fits_i64() && c.a32.fits_i64() &&
+                      c.a33.fits_i64() && o.denom.fits_i64()))
+                    raise_overflow();
+                out[0] = c.a11.low64(); out[1] = c.a12.low64(); out[2] = c.a13.low64();
+                out[3] = c.a21.low64(); out[4] = c.a22.low64(); out[5] = c.a23.low64();
+                out[6] = c.a31.low64(); out[7] = c.a32.low64(); out[8] = c.a33.low64();
+                out[9] = o.denom.low64(); out[10] = n; out[11] = o.r;
+            }
+        }
+    }
+
+    __syncthreads();
+    if (threadIdx.x == 0 && *cta_flag_ptr())
+        atomicMin(L.err + 0, (u64)blockIdx.x * TB_NBR_THREADS);
+}
+
+// ---------------------------------------------------------------------------
+// Block-wide exclusive prefix sum of one int per thread (blockDim <= 1024).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums, int &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        int y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0)
+    {
+        const int nw = (blockDim.x + 31) >> 5;
+        int w = lane < nw ? warp_sums[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            int y = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += y;
+        }
+        warp_sums[lane] = wi - w;          // exclusive warp offsets
+        if (lane == 31) warp_sums[32] = wi;   // grand total
+    }
+    __syncthreads();
+    const int out = warp_sums[warp] + incl - v;
+    total = warp_sums[32];
+    __syncthreads();
+    return out;
+}
+
+// ---------------------------------------------------------------------------
+// rows_kernel: one CTA per representative row; all 2^K conductors.
+//
+// The p+1 packed words of the row are counting-sorted by r with a bitmask over
+// the genus (rank = popcount prefix), so each distinct r becomes one column j
+// holding a run of spins.  For conductor k the row entry of column j is
+//     sum_i chi_k(spin_i) = run - 2 * #{i : popc(spin_i & k) odd}        birch_util.h:81-91
+// kept if lut[k][r] != -1 and the sum is nonzero.                         Genus.h:628-653
+// FILL = false counts the nonzeros per (k, row); FILL = true writes them at
+// indptr offsets (ascending columns, zeros dropped).
+// ---------------------------------------------------------------------------
+struct RowLaunch {
+    int N, K;
+    int rep_begin, rows;
+    u32 P1;
+    int mask_words;        // ceil(N / 32)
+    const u32 *W;          // [rows][P1]
+    const int *lut;        // [2^K][N]
+    const int *rowbase;    // [2^K] offset of conductor k's indptr block in indptr_all
+    const int *rowfirst;   // [2^K] lut[k][first included rep >= rep_begin] (row index of the shard's first row)
+    int *indptr_all;       // concatenated (rows_k + 1) blocks
+    const i64 *nnzbase;    // [2^K] offset of conductor k in data/indices (FILL)
+    int *data;
+    int *indices;
+};
+
+template <bool FILL>
+__global__ void rows_kernel(const __grid_constant__ RowLaunch L)
+{
+    extern __shared__ u32 smem[];
+    // layout: mask[mw] | wprefix[mw] | start[maxcols+1] | colr[maxcols] | warp_sums[33] | spins (u16)[P1]
+    const int mw = L.mask_words;
+    const int maxcols = min((int)L.P1, L.N);
+    u32 *mask = smem;
+    u32 *wprefix = mask + mw;
+    int *start = (int *)(wprefix + mw);
+    int *colr = start + maxcols + 1;
+    int *warp_sums = colr + maxcols;
+    unsigned short *spins = (unsigned short *)(warp_sums + 36);
+
+    const int lrow = blockIdx.x;
+    const int n = L.rep_begin + lrow;
+    const u32 *Wrow = L.W + (size_t)lrow * L.P1;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const u32 spin_mask = (1u << L.K) - 1u;
+
+    for (int i = tid; i < mw; i += nt) mask[i] = 0u;
+    for (int i = tid; i <= maxcols; i += nt) start[i] = 0;
+    __syncthreads();
+
+    // touched representatives
+    // (a failed neighbor carries 0xffffffff: r >= N, skipped everywhere below)
+    for (u32 t = tid; t < L.P1; t += nt)
+    {
+        u32 r = Wrow[t] >> L.K;
+        if (r < (u32)L.N) atomicOr(&mask[r >> 5], 1u << (r & 31));
+    }
+    __syncthreads();
+
+    // popcount prefix over mask words -> rank of every touched r
+    int carry = 0;
+    for (int base = 0; base < mw; base += nt)
+    {
+        int i = base + tid;
+        int c = i < mw ? __popc(mask[i]) : 0;
+        int total;
+        int ex = block_exclusive_scan(c, warp_sums, total);
+        if (i < mw) wprefix[i] = carry + ex;
+        carry += total;
+    }
+    const int ncols = carry;
+    __syncthreads();
+
+    // run lengths, then run starts
+    for (u32 t = tid; t < L.P1; t += nt)
+    {
+        u32 r = Wrow[t] >> L.K;
+        if (r >= (u32)L.N) continue;
+        int j = wprefix[r >> 5] + __popc(mask[r >> 5] & ((1u << (r & 31)) - 1u));
+        atomicAdd(&start[j + 1], 1);
+    }
+    // column -> representative
+    for (int i = tid; i < mw; i += nt)
+    {
+        u32 m = mask[i];
+        int j = wprefix[i];
+        while (m)
+        {
+            int b = __ffs(m) - 1;
+            colr[j++] = i * 32 + b;
+            m &= m - 1;
+        }
+    }
+    __syncthreads();
+    carry = 0;
+    for (int base = 0; base < ncols; base += nt)
+    {
+        int j = base + tid;
+        int c = j < ncols ? start[j + 1] : 0;
+        int total;
+        int ex = block_exclusive_scan(c, warp_sums, total);
+        if (j < ncols) start[j + 1] = carry + ex + c;   // inclusive end
+        carry += total;
+    }
+    const int nvalid = carry;
+    __syncthreads();
+    // scatter spins into their runs, filling each run from its end backwards
+    for (u32 t = tid; t < L.P1; t += nt)
+    {
+        u32 w = Wrow[t];
+        u32 r = w >> L.K;
+        if (r >= (u32)L.N) continue;
+        int j = wprefix[r >> 5] + __popc(mask[r >> 5] & ((1u << (r & 31)) - 1u));
+        int slot = atomicSub(&start[j + 1], 1) - 1;
+        spins[slot] = (unsigned short)(w & spin_mask);
+    }
+    __syncthreads();
+    // now start[j+1] == begin of run j; the end of run j is the begin of run j+1, nvalid for the last
+    // (start[0] is unused by the scatter and still 0)
+
+    const int C = 1 << L.K;
+    for (int k = 0; k < C; ++k)
+    {
+        const int *lut = L.lut + (size_t)k * L.N;
+        const int npos = lut[n];
+        if (npos == -1) continue;                    // Genus.h:624-625
+        const int out_row = npos - L.rowfirst[k];
+        int *indptr = L.indptr_all + L.rowbase[k];
+        i64 wbase = 0;
+        if (FILL) wbase = L.nnzbase[k] + indptr[out_row];
+
+        int row_total = 0;
+        for (int base = 0; base < ncols; base += nt)
+        {
+            const int j = base + tid;
+            int value = 0, rpos = -1;
+            if (j < ncols)
+            {
+                rpos = lut[colr[j]];
+                if (rpos != -1)
+                {
+                    const int b = start[j + 1];
+                    const int e = (j + 1 < ncols) ? start[j + 2] : nvalid;
+                    int odd = 0;
+                    for (int i = b; i < e; ++i) odd += __popc((u32)spins[i] & (u32)k) & 1;
+                    value = (e - b) - 2 * odd;
+                }
+            }
+            const int flag = value != 0;
+            int total;
+            const int ex = block_exclusive_scan(flag, warp_sums, total);
+            if (FILL && flag)
+            {
+                L.data[wbase + row_total + ex] = value;
+                L.indices[wbase + row_total + ex] = rpos;
+            }
+            row_total += total;
+        }
+        if (!FILL && tid == 0) indptr[out_row + 1] = row_total;
+    }
+}
+
+// In-place inclusive scan of each conductor's (rows_k + 1) block; one CTA per
+// conductor.  Also emits nnz[k].
+__global__ void indptr_scan_kernel(int *indptr_all, const int *rowbase, const int *rowcount, i64 *nnz)
+{
+    __shared__ int warp_sums[36];
+    const int k = blockIdx.x;
+    int *indptr = indptr_all + rowbase[k];
+    const int rows = rowcount[k];
+    int carry = 0;
+    for (int base = 0; base < rows; base += blockDim.x)
+    {
+        int i = base + threadIdx.x;
+        int c = i < rows ? indptr[i + 1] : 0;
+        int total;
+        int ex = block_exclusive_scan(c, warp_sums, total);
+        if (i < rows) indptr[i + 1] = carry + ex + c;
+        carry += total;
+    }
+    if (threadIdx.x == 0) { indptr[0] = 0; nnz[k] = carry; }
+}
+
+// Dense rows from the CSR rows of one conductor.
+__global__ void dense_scatter_kernel(const int *indptr, const int *data, const int *indices, int rows, int dim, int *matrix)
+{
+    const int row = blockIdx.x;
+    if (row >= rows) return;
+    for (int i = indptr[row] + threadIdx.x; i < indptr[row + 1]; i += blockDim.x)
+        matrix[(size_t)row * dim + indices[i]] = data[i];
+}
+
+// ---------------------------------------------------------------------------
+// Eigenvalue accumulation for one representative.  Genus.h:490-499.
+//   out[v] += chi_{cond[v]}(spin_t) * vecs[v][r_t]   for every vector listed in sel[]
+// ---------------------------------------------------------------------------
+__global__ void eigen_dot_kernel(const u32 *W, u32 P1, int K, int N, const int *vecs, const i64 *cond,
+                                 const int *sel, int nsel, int *out)
+{
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = t < P1;
+    u32 w = live ? W[t] : 0u;
+    const u32 r = w >> K, spin = w & ((1u << K) - 1u);
+    live = live && r < (u32)N;
+    for (int s = 0; s < nsel; ++s)
+    {
+        const int v = sel[s];
+        int term = 0;
+        if (live)
+        {
+            const int coord = vecs[(size_t)v * N + r];
+            term = (__popc(spin & (u32)cond[v]) & 1) ? -coord : coord;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) term += __shfl_xor_sync(0xffffffffu, term, d);
+        if ((threadIdx.x & 31) == 0 && term != 0) atomicAdd(out + v, term);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Integer-pipe microbenchmark: the roofline denominator.  Dependent chains of
+// IMAD (fma pipe) and IADD3/LOP3 (alu pipe), 8 independent chains per thread.
+// ---------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) int_peak_kernel(u32 *sink, int iters, u32 seed)
+{
+    u32 x0 = seed + threadIdx.x, x1 = x0 * 3u + 1u, x2 = x0 * 5u + 2u, x3 = x0 * 7u + 3u;
+    u32 x4 = x0 * 11u + 4u, x5 = x0 * 13u + 5u, x6 = x0 * 17u + 6u, x7 = x0 * 19u + 7u;
+    const u32 m = seed | 1u, c = seed ^ 0x9e3779b9u;
+    for (int i = 0; i < iters; ++i)
+    {
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+        {
+            if (KIND == 0 || KIND == 2)
+            {
+                x0 = x0 * m + c; x1 = x1 * m + c; x2 = x2 * m + c; x3 = x3 * m + c;
+                x4 = x4 * m + c; x5 = x5 * m + c; x6 = x6 * m + c; x7 = x7 * m + c;
+            }
+            if (KIND == 1 || KIND == 2)
+            {
+                x0 = (x0 ^ c) + (x1 & m); x1 = (x1 ^ c) + (x2 & m); x2 = (x2 ^ c) + (x3 & m); x3 = (x3 ^ c) + (x4 & m);
+                x4 = (x4 ^ c) + (x5 & m); x5 = (x5 ^ c) + (x6 & m); x6 = (x6 ^ c) + (x7 & m); x7 = (x7 ^ c) + (x0 & m);
+            }
+        }
+    }
+    u32 r = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+    if (r == 0x12345678u) sink[0] = r;
+}
+
+}  // namespace tb

@@ -1,0 +1,688 @@
+// tb_neighbor.cuh -- one p-neighbor, start to finish, in registers (sm_100a).
+//
+// Device-side building blocks of the hot path:
+//   line_for_t        t -> isotropic line mod p      NeighborManager.h:50-144, 370-394
+//   build_neighbor    lattice + isometry             NeighborManager.h:207-356
+//   eisenstein_reduce unique reduced representative  QuadForm.h:530-767
+//   genus_lookup      open-addressing probe          HashMap.h:68-89, QuadForm.cpp:779-803
+//   spinor_norm       spinor/Kronecker class         Spinor.h:19-66, Genus.h:582-615
+// One thread owns one neighbor.  All of it is templated on the integer mode Z
+// (W64 | C128, tb_int.cuh).
+#pragma once
+
+#include "tb_int.cuh"
+
+namespace tb {
+
+// ---------------------------------------------------------------------------
+// Launch-invariant context.
+// ---------------------------------------------------------------------------
+#define TB_MAX_PRIMES 16
+
+// Per-representative record, one 128-byte line each.
+//   cur[n]: q[6], scalar, s[9]      (data of the representative being expanded)
+//   rep[r]: q[6], scalar, sinv[9]   (data of the representative that is hit)
+#define TB_REC_WORDS 16
+
+// Per (representative, prime) record written by prep_reps_kernel.
+struct RepPrime {
+    u32 a, b, h;      // coefficients mod p
+    u32 x0, y0;       // conic base point (x0, y0, 1); p = 2: packed vectors 0 and 1
+    u32 a0, delta;    // NeighborManager.h:34-47; p = 2: a0 = packed vector 2
+    u32 pad;
+};
+
+struct PrimeCtx {
+    u32 p;
+    u32 use_lut;
+    u64 pp;
+    InvDiv dp;        // division by p
+    InvDiv dpp;       // division by p^2
+    const u32 *inv_lut;   // [p] inverses mod p, or nullptr
+};
+
+struct GenusCtx {
+    int N;
+    int K;
+    u32 slot_mask;
+    u32 pad;
+    const i64 *cur;       // [N][16]
+    const i64 *rep;       // [N][16]
+    const i64 *disc;      // [N] wrap-around discriminant of each representative
+    const int *slots;     // [slot_mask+1] representative index or -1
+    InvDiv spin[TB_MAX_PRIMES];   // the level's prime divisors
+};
+
+template <class Z>
+struct Form {
+    Z a, b, c, f, g, h;
+};
+
+// 3x3 integer matrix, row-major (Isometry.h:350-354).  The methods are the
+// column operations reduce/build apply; the comment gives the reference's name.
+template <class Z>
+struct Iso {
+    Z a11, a12, a13, a21, a22, a23, a31, a32, a33;
+
+    // col3 += col1 + col2                                    A101011001
+    __device__ __forceinline__ void c3_add_c1_c2() { a13 += a11 + a12; a23 += a21 + a22; a33 += a31 + a32; }
+    // col2 += t col1                                          A1t0010001
+    __device__ __forceinline__ void c2_add_c1(Z t) { a12 += t * a11; a22 += t * a21; a32 += t * a31; }
+    // col3 += t col2                                          A10001t001
+    __device__ __forceinline__ void c3_add_c2(Z t) { a13 += t * a12; a23 += t * a22; a33 += t * a32; }
+    // col3 += t col1                                          A10t010001
+    __device__ __forceinline__ void c3_add_c1(Z t) { a13 += t * a11; a23 += t * a21; a33 += t * a31; }
+    // (c1, c2, c3) <- (-c2, -c1, -c3)                         A0n0n0000n
+    __device__ __forceinline__ void swap12_neg()
+    {
+        Z t;
+        t = -a11; a11 = -a12; a12 = t; a13 = -a13;
+        t = -a21; a21 = -a22; a22 = t; a23 = -a23;
+        t = -a31; a31 = -a32; a32 = t; a33 = -a33;
+    }
+    // (c1, c2, c3) <- (-c1, -c3, -c2)                         An0000n0n0
+    __device__ __forceinline__ void swap23_neg()
+    {
+        Z t;
+        t = -a12; a12 = -a13; a13 = t; a11 = -a11;
+        t = -a22; a22 = -a23; a23 = t; a21 = -a21;
+        t = -a32; a32 = -a33; a33 = t; a31 = -a31;
+    }
+    __device__ __forceinline__ void neg_c1() { a11 = -a11; a21 = -a21; a31 = -a31; }   // An00010001
+    __device__ __forceinline__ void neg_c2() { a12 = -a12; a22 = -a22; a32 = -a32; }   // A1000n0001
+    __device__ __forceinline__ void neg_c3() { a13 = -a13; a23 = -a23; a33 = -a33; }   // A10001000n
+    // c3 += c1 + c2; c1 = -c1; c2 = -c2                       An010n1001
+    __device__ __forceinline__ void fix_sum()
+    {
+        a13 += a11 + a12; a11 = -a11; a12 = -a12;
+        a23 += a21 + a22; a21 = -a21; a22 = -a22;
+        a33 += a31 + a32; a31 = -a31; a32 = -a32;
+    }
+    // c2 = -(c2 + c1); c1 = -c1                               Ann00n0001
+    __device__ __forceinline__ void fix_ah()
+    {
+        a12 += a11; a12 = -a12; a11 = -a11;
+        a22 += a21; a22 = -a22; a21 = -a21;
+        a32 += a31; a32 = -a32; a31 = -a31;
+    }
+    // c3 = -(c3 + c1); c1 = -c1                               An0n01000n
+    __device__ __forceinline__ void fix_ag()
+    {
+        a13 += a11; a13 = -a13; a11 = -a11;
+        a23 += a21; a23 = -a23; a21 = -a21;
+        a33 += a31; a33 = -a33; a31 = -a31;
+    }
+    // c3 = -(c3 + c2); c2 = -c2                               A1000nn00n
+    __device__ __forceinline__ void fix_bf()
+    {
+        a13 += a12; a13 = -a13; a12 = -a12;
+        a23 += a22; a23 = -a23; a22 = -a22;
+        a33 += a32; a33 = -a33; a32 = -a32;
+    }
+    // c2 -= c1; c1 = -c1; c3 = -c3                            Ann001000n
+    __device__ __forceinline__ void edge_ah()
+    {
+        a12 -= a11; a11 = -a11; a13 = -a13;
+        a22 -= a21; a21 = -a21; a23 = -a23;
+        a32 -= a31; a31 = -a31; a33 = -a33;
+    }
+    // c3 -= c1; c1 = -c1; c2 = -c2                            An0n0n0001
+    __device__ __forceinline__ void edge_ag()
+    {
+        a13 -= a11; a11 = -a11; a12 = -a12;
+        a23 -= a21; a21 = -a21; a22 = -a22;
+        a33 -= a31; a31 = -a31; a32 = -a32;
+    }
+    // c3 -= c2; c2 = -c2; c1 = -c1                            An000nn001
+    __device__ __forceinline__ void edge_bf()
+    {
+        a13 -= a12; a12 = -a12; a11 = -a11;
+        a23 -= a22; a22 = -a22; a21 = -a21;
+        a33 -= a32; a32 = -a32; a31 = -a31;
+    }
+    // (c2, c3) <- (-c3, c2)                                   A1000010n0
+    __device__ __forceinline__ void rot23()
+    {
+        Z t;
+        t = a13; a13 = a12; a12 = -t;
+        t = a23; a23 = a22; a22 = -t;
+        t = a33; a33 = a32; a32 = -t;
+    }
+    // col2 += t col3                                          A1000100t1
+    __device__ __forceinline__ void c2_add_c3(Z t) { a12 += a13 * t; a22 += a23 * t; a32 += a33 * t; }
+    // col1 += t col3                                          A100010t01
+    __device__ __forceinline__ void c1_add_c3(Z t) { a11 += a13 * t; a21 += a23 * t; a31 += a33 * t; }
+    // col2 *= p, col3 *= p^2                                  A1000p000p2
+    __device__ __forceinline__ void scale_p(Z p, Z pp)
+    {
+        a12 *= p; a22 *= p; a32 *= p;
+        a13 *= pp; a23 *= pp; a33 *= pp;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Fp on canonical residues, p < 2^31.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ u32 fp_mul(u32 a, u32 b, const PrimeCtx &pc)
+{
+    u64 r;
+    udivmod((u64)a * (u64)b, pc.dp, r);
+    return (u32)r;
+}
+__device__ __forceinline__ u32 fp_add(u32 a, u32 b, u32 p) { u32 s = a + b; return s >= p ? s - p : s; }
+__device__ __forceinline__ u32 fp_sub(u32 a, u32 b, u32 p) { return a >= b ? a - b : a + p - b; }
+__device__ __forceinline__ u32 fp_pow(u32 a, u32 e, const PrimeCtx &pc)
+{
+    u32 r = 1;
+    while (e)
+    {
+        if (e & 1u) r = fp_mul(r, a, pc);
+        a = fp_mul(a, a, pc);
+        e >>= 1;
+    }
+    return r;
+}
+// Fp::inverse (Fp.h:147-150): table below 2^22 (built per prime by
+// inverse_lut_kernel), Fermat above.  F2::inverse for p = 2.
+__device__ __forceinline__ u32 fp_inv(u32 a, const PrimeCtx &pc)
+{
+    if (pc.p == 2u) return a & 1u;
+    if (pc.use_lut) return __ldg(pc.inv_lut + a);
+    return a ? fp_pow(a, pc.p - 2u, pc) : 0u;
+}
+// Fp::mod of a signed 64-bit coefficient (Fp.h:29-35).
+__device__ __forceinline__ u32 fp_mod_i64(i64 x, const PrimeCtx &pc)
+{
+    u64 r;
+    udivmod(x < 0 ? 0ull - (u64)x : (u64)x, pc.dp, r);
+    if (x < 0 && r != 0) r = pc.p - r;
+    return (u32)r;
+}
+
+// ---------------------------------------------------------------------------
+// t -> isotropic line.  NeighborManager::isotropic_vector, NeighborManager.h:50-144;
+// p = 2: isotropic_vector_p2, 370-394.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void line_for_t(const RepPrime &rp, u32 t, const PrimeCtx &pc,
+                                           u32 &vx, u32 &vy, u32 &vz)
+{
+    const u32 p = pc.p;
+    if (p == 2u)
+    {
+        u32 w = t == 0 ? rp.x0 : (t == 1 ? rp.y0 : rp.a0);
+        vz = w & 1u; vy = (w >> 1) & 1u; vx = (w >> 2) & 1u;
+        return;
+    }
+    if (t == p)
+    {
+        u32 at = fp_sub(rp.delta, rp.h, p);
+        if (at == 0) { vx = rp.x0; vy = rp.y0 ? rp.y0 - 1 : p - 1; vz = 1; }
+        else if (rp.b == 0) { vx = 0; vy = 1; vz = 0; }
+        else
+        {
+            u32 inv = fp_mul(fp_inv(rp.b, pc), at, pc);
+            vx = rp.x0; vy = fp_add(rp.y0, fp_sub(inv, 1, p), p); vz = 1;
+        }
+        return;
+    }
+    // at = ((t-1) b + delta) t + a0   (equals a0 at t = 0 and a0 + delta at t = 1)
+    u32 at = fp_mul(fp_add(fp_mul(fp_sub(t, 1, p), rp.b, pc), rp.delta, p), t, pc);
+    at = fp_add(at, rp.a0, p);
+    if (at == 0)
+    {
+        vx = rp.x0 ? rp.x0 - 1 : p - 1; vy = fp_sub(rp.y0, t, p); vz = 1;
+        return;
+    }
+    // ct = (b t + h) t + a = Q(1, t, 0)
+    u32 ct = fp_add(fp_mul(fp_add(fp_mul(rp.b, t, pc), rp.h, p), t, pc), rp.a, p);
+    if (ct == 0)
+    {
+        if (t == 0) { vx = 1; vy = 0; vz = 0; }
+        else { vx = fp_inv(t, pc); vy = 1; vz = 0; }
+        return;
+    }
+    u32 inv = fp_mul(at, fp_inv(ct, pc), pc);
+    vx = fp_add(rp.x0, fp_sub(inv, 1, p), p);
+    vy = fp_add(fp_sub(rp.y0, t, p), fp_mul(t, inv, pc), p);
+    vz = 1;
+}
+
+// ---------------------------------------------------------------------------
+// Neighbor lattice.  NeighborManager::build_neighbor, NeighborManager.h:207-356.
+// Returns false when the int64 discriminant check (344-354) fails.
+// ---------------------------------------------------------------------------
+template <class Z>
+struct CheckDisc { static const bool value = false; };
+template <>
+struct CheckDisc<W64> { static const bool value = true; };
+
+template <class Z>
+__device__ __forceinline__ Z form_disc(const Form<Z> &q)
+{
+    // QuadForm.h:27-32
+    return q.a * (Z(4) * q.b * q.c - q.f * q.f) - q.b * q.g * q.g + q.h * (q.f * q.g - q.c * q.h);
+}
+
+template <class Z>
+__device__ __forceinline__ bool build_neighbor(const Form<Z> &q, u32 vx, u32 vy, u32 vz, i64 disc64,
+                                               const PrimeCtx &pc, Form<Z> &out, Iso<Z> &s)
+{
+    const Z p = Z((i64)pc.p);
+    const Z pp = Z((i64)pc.pp);
+    const i64 half = (i64)(pc.p >> 1);
+    Z aa, bb, cc, ff, gg, hh;
+
+    // balanced lifts of the line's coordinates (223-224)
+    i64 ux = (i64)vx, uy = (i64)vy;
+    if (ux > half) ux -= (i64)pc.p;
+    if (uy > half) uy -= (i64)pc.p;
+    const Z zero = Z(0), one = Z(1), mone = Z(-1);
+
+    if (vz == 1u)                                            // 226-245
+    {
+        Z u = Z(ux), v = Z(uy);
+        s.a11 = u; s.a12 = zero; s.a13 = mone;
+        s.a21 = v; s.a22 = one; s.a23 = zero;
+        s.a31 = one; s.a32 = zero; s.a33 = zero;
+        Z au = q.a * u, hu = q.h * u, hv = q.h * v, bv = q.b * v;
+        Z temp = au + hv + q.g;
+        aa = q.c + u * temp + v * (bv + q.f);
+        bb = q.b;
+        cc = q.a;
+        ff = -q.h;
+        gg = -(temp + au);
+        hh = q.f + hu + bv.twice();
+    }
+    else if (uy == 1)                                        // 246-261
+    {
+        Z u = Z(ux);
+        s.a11 = u; s.a12 = zero; s.a13 = one;
+        s.a21 = one; s.a22 = zero; s.a23 = zero;
+        s.a31 = zero; s.a32 = one; s.a33 = zero;
+        Z au = q.a * u, gu = q.g * u;
+        Z temp = au + q.h;
+        aa = q.b + u * temp;
+        bb = q.c;
+        cc = q.a;
+        ff = q.g;
+        gg = temp + au;
+        hh = q.f + gu;
+    }
+    else                                                     // 262-272
+    {
+        s.a11 = one; s.a12 = zero; s.a13 = zero;
+        s.a21 = zero; s.a22 = zero; s.a23 = mone;
+        s.a31 = zero; s.a32 = one; s.a33 = zero;
+        aa = q.a; bb = q.c; cc = q.b;
+        ff = -q.f; gg = -q.h; hh = q.g;
+    }
+
+    Z gmodp = trunc_rem(gg, pc.dp);                          // 279-295
+    if (gmodp.is_zero())
+    {
+        s.rot23();
+        Z t = bb; bb = cc; cc = t;
+        t = gg; gg = hh; hh = -t;
+        ff = -ff;
+        gmodp = trunc_rem(gg, pc.dp);
+    }
+    if (gmodp.is_neg()) gmodp += p;                          // 302
+    const Z ginv = Z((i64)fp_inv((u32)gmodp.low64(), pc));   // 303
+
+    Z s1 = trunc_rem((-hh) * ginv, pc.dp);                   // 309-312
+    Z s2 = trunc_rem((-aa) * ginv, pc.dpp);
+    if (s1 < Z(-half)) s1 += p;
+    if (s2 < Z(-(i64)(pc.pp >> 1))) s2 += pp;
+
+    s.c2_add_c3(s1);                                         // 314-319
+    Z temp1 = cc * s1;
+    bb += s1 * (ff + temp1);
+    ff += temp1.twice();
+    hh += s1 * gg;
+
+    s.c1_add_c3(s2);                                         // 325-329
+    Z temp2 = cc * s2;
+    aa += s2 * (gg + temp2);
+    gg += temp2.twice();
+    hh += s2 * ff;
+
+    s.scale_p(p, pp);                                        // 337-341
+    aa = trunc_div(aa, pc.dpp);
+    cc *= pp;
+    ff *= p;
+    hh = trunc_div(hh, pc.dp);
+
+    out.a = aa; out.b = bb; out.c = cc; out.f = ff; out.g = gg; out.h = hh;
+
+    if (CheckDisc<Z>::value)                                 // 344-354
+        return form_disc(out).low64() == disc64;
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// Eisenstein reduction with isometry tracking.  QuadForm<R>::reduce,
+// QuadForm.h:530-767 (GMP twin: QuadForm.cpp:69-379).  The statement order is
+// the reference's: the isometry (not the reduced form) depends on it.
+// Returns false when the iteration cap trips (wrapped garbage only).
+// ---------------------------------------------------------------------------
+#define TB_REDUCE_CAP 256
+
+template <class Z>
+__device__ __forceinline__ Z shear_quotient(Z a, Z h)
+{
+    // t = a >= h ? (a-h) div 2a : -((a+h-1) div 2a)         551-558
+    Z den = a.twice();
+    if (a >= h) return ref_quotient(a - h, den);
+    return -ref_quotient(a + h - Z(1), den);
+}
+
+template <class Z>
+__device__ __forceinline__ bool eisenstein_reduce(Form<Z> &q, Iso<Z> &s)
+{
+    Z a = q.a, b = q.b, c = q.c, f = q.f, g = q.g, h = q.h;
+    Z t;
+    const Z zero = Z(0);
+    int iters = 0;
+    bool again = true;
+    while (again)
+    {
+        if (++iters > TB_REDUCE_CAP) return false;
+
+        t = a + b + f + g + h;                               // 542-549
+        if (t < zero)
+        {
+            s.c3_add_c1_c2();
+            c += t;
+            f += h + b.twice();
+            g += h + a.twice();
+        }
+
+        t = shear_quotient(a, h);                            // 551-567
+        if (!t.is_zero())
+        {
+            s.c2_add_c1(t);
+            Z temp = a * t;
+            h += temp;
+            b += h * t;
+            f += g * t;
+            h += temp;
+        }
+
+        t = shear_quotient(b, f);                            // 569-585
+        if (!t.is_zero())
+        {
+            s.c3_add_c2(t);
+            Z temp = b * t;
+            f += temp;
+            c += f * t;
+            g += h * t;
+            f += temp;
+        }
+
+        t = shear_quotient(a, g);                            // 587-603
+        if (!t.is_zero())
+        {
+            s.c3_add_c1(t);
+            Z temp = a * t;
+            g += temp;
+            c += g * t;
+            f += h * t;
+            g += temp;
+        }
+
+        if (a > b || (a == b && f.abs() > g.abs()))          // 605-610
+        {
+            s.swap12_neg();
+            t = a; a = b; b = t;
+            t = f; f = g; g = t;
+        }
+        if (b > c || (b == c && g.abs() > h.abs()))          // 612-617
+        {
+            s.swap23_neg();
+            t = b; b = c; c = t;
+            t = g; g = h; h = t;
+        }
+        if (a > b || (a == b && f.abs() > g.abs()))          // 619-624
+        {
+            s.swap12_neg();
+            t = a; a = b; b = t;
+            t = f; f = g; g = t;
+        }
+
+        // sign normalisation                                  626-687
+        const bool fneg = f.is_neg(), gneg = g.is_neg(), hneg = h.is_neg();
+        const bool fz = f.is_zero(), gz = g.is_zero(), hz = h.is_zero();
+        bool fgh = !fz && !gz && !hz;
+        if (fgh) fgh = ((int)fneg + (int)gneg + (int)hneg) % 2 == 0;
+        bool n1, n2, n3;
+        if (fgh) { n1 = fneg; n2 = gneg; n3 = hneg; }
+        else
+        {
+            int s1 = !fneg && !fz, s2 = !gneg && !gz, s3 = !hneg && !hz;
+            if ((s1 + s2 + s3) % 2 == 1)
+            {
+                if (fz) s1 = 1;
+                else if (gz) s2 = 1;
+                else if (hz) s3 = 1;
+            }
+            n1 = s1 == 1; n2 = s2 == 1; n3 = s3 == 1;
+        }
+        if (n1) { s.neg_c1(); f = -f; }
+        if (n2) { s.neg_c2(); g = -g; }
+        if (n3) { s.neg_c3(); h = -h; }
+
+        again = !(f.abs() <= b && g.abs() <= a && h.abs() <= a && a + b + f + g + h >= zero);   // 689-690
+    }
+
+    Z sum = a + b + f + g + h;
+    if (sum.is_zero() && a.twice() + g.twice() + h > zero)   // 693-700
+    {
+        s.fix_sum();
+        c += sum;
+        f += h + b.twice(); f = -f;
+        g += h + a.twice(); g = -g;
+    }
+    if (a == -h && !g.is_zero())                             // 702-708
+    {
+        s.fix_ah();
+        f += g; f = -f;
+        g = -g;
+        h = -h;
+    }
+    if (a == -g && !h.is_zero())                             // 710-716
+    {
+        s.fix_ag();
+        f += h; f = -f;
+        h = -h;
+        g += a.twice();
+    }
+    if (b == -f && !h.is_zero())                             // 718-724
+    {
+        s.fix_bf();
+        g += h; g = -g;
+        h = -h;
+        f += b.twice();
+    }
+    if (a == h && g > f.twice()) { s.edge_ah(); f = g - f; }   // 726-730
+    if (a == g && h > f.twice()) { s.edge_ag(); f = h - f; }   // 732-736
+    if (b == f && h > g.twice()) { s.edge_bf(); g = h - g; }   // 738-742
+    if (a == b && f.abs() > g.abs())                         // 744-750
+    {
+        s.swap12_neg();
+        t = a; a = b; b = t;
+        t = g; g = f; f = t;
+    }
+    if (b == c && g.abs() > h.abs())                         // 752-757
+    {
+        s.swap23_neg();
+        t = g; g = h; h = t;
+    }
+    if (a == b && f.abs() > g.abs())                         // 759-764
+    {
+        s.swap12_neg();
+        t = g; g = f; f = t;
+    }
+
+    q.a = a; q.b = b; q.c = c; q.f = f; q.g = g; q.h = h;
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// Genus lookup.  QuadForm::hash_value (QuadForm.cpp:779-803) + HashMap::indexof
+// (HashMap.h:68-89).  Returns the representative index or -1 ("Key not found.").
+// ---------------------------------------------------------------------------
+template <class Z>
+__device__ __forceinline__ int genus_lookup(const Form<Z> &q, const GenusCtx &gc)
+{
+    if (!(q.a.fits_i64() && q.b.fits_i64() && q.c.fits_i64() &&
+          q.f.fits_i64() && q.g.fits_i64() && q.h.fits_i64()))
+        return -1;
+    const i64 k0 = q.a.low64(), k1 = q.b.low64(), k2 = q.c.low64();
+    const i64 k3 = q.f.low64(), k4 = q.g.low64(), k5 = q.h.low64();
+    u64 fnv = 0x811c9dc5ull;
+    fnv = (fnv ^ (u64)k0) * 0x01000193ull;
+    fnv = (fnv ^ (u64)k1) * 0x01000193ull;
+    fnv = (fnv ^ (u64)k2) * 0x01000193ull;
+    fnv = (fnv ^ (u64)k3) * 0x01000193ull;
+    fnv = (fnv ^ (u64)k4) * 0x01000193ull;
+    fnv = (fnv ^ (u64)k5) * 0x01000193ull;
+    u32 slot = (u32)fnv & gc.slot_mask;
+    for (u32 probes = 0; probes <= gc.slot_mask; ++probes)
+    {
+        int idx = __ldg(gc.slots + slot);
+        if (idx < 0) return -1;
+        const longlong2 *key = reinterpret_cast<const longlong2 *>(gc.rep + (size_t)idx * TB_REC_WORDS);
+        longlong2 x = __ldg(key), y = __ldg(key + 1), z = __ldg(key + 2);
+        if (x.x == k0 && x.y == k1 && y.x == k2 && y.y == k3 && z.x == k4 && z.y == k5) return idx;
+        slot = (slot + 1) & gc.slot_mask;
+    }
+    return -1;
+}
+
+// ---------------------------------------------------------------------------
+// Spinor norm class.  Spinor::compute_vals (Spinor.h:52-66) and Spinor::norm
+// (Spinor.h:19-41).
+// ---------------------------------------------------------------------------
+template <class Z>
+__device__ __forceinline__ u32 prime_parities(Z x, const GenusCtx &gc)
+{
+    u32 val = 0;
+    if (x.is_zero()) { raise_overflow(); return 0; }   // the reference's loop would not terminate
+    for (int i = 0; i < gc.K; ++i)
+    {
+        const InvDiv &iv = gc.spin[i];
+        while (strip_factor(x, iv)) val ^= (1u << i);
+    }
+    return val;
+}
+
+template <class Z>
+__device__ __forceinline__ u32 spinor_norm(const Form<Z> &q, const Iso<Z> &s, Z scalar, const GenusCtx &gc)
+{
+    const u32 twist = (1u << gc.K) - 1u;
+    Z tr = s.a11 + s.a22 + s.a33;
+    if (tr != -scalar) return prime_parities(tr + scalar, gc);
+
+    Z delta = (q.a * (s.a22 + s.a33)).twice() - (q.g * s.a31 + q.h * s.a21);
+    if (!delta.is_zero()) return prime_parities(delta, gc) ^ twist;
+
+    Z abh = Z(4) * q.a * q.b - q.h * q.h;
+    Z abhm33 = abh * s.a33 + s.a32 * (q.g * q.h - (q.a * q.f).twice()) + s.a31 * (q.f * q.h - (q.b * q.g).twice());
+    if (abhm33 != abh * scalar)
+        return prime_parities(abhm33 - abh * scalar, gc) ^ prime_parities(q.a.twice(), gc) ^ twist;
+
+    return prime_parities(abh * scalar, gc);
+}
+
+template <class Z>
+__device__ __forceinline__ Iso<Z> iso_mul(const Iso<Z> &x, const Iso<Z> &y)
+{
+    // Isometry.h:63-76
+    Iso<Z> t;
+    t.a11 = x.a11 * y.a11 + x.a12 * y.a21 + x.a13 * y.a31;
+    t.a12 = x.a11 * y.a12 + x.a12 * y.a22 + x.a13 * y.a32;
+    t.a13 = x.a11 * y.a13 + x.a12 * y.a23 + x.a13 * y.a33;
+    t.a21 = x.a21 * y.a11 + x.a22 * y.a21 + x.a23 * y.a31;
+    t.a22 = x.a21 * y.a12 + x.a22 * y.a22 + x.a23 * y.a32;
+    t.a23 = x.a21 * y.a13 + x.a22 * y.a23 + x.a23 * y.a33;
+    t.a31 = x.a31 * y.a11 + x.a32 * y.a21 + x.a33 * y.a31;
+    t.a32 = x.a31 * y.a12 + x.a32 * y.a22 + x.a33 * y.a32;
+    t.a33 = x.a31 * y.a13 + x.a32 * y.a23 + x.a33 * y.a33;
+    return t;
+}
+
+template <class Z>
+__device__ __forceinline__ Form<Z> load_form(const i64 *rec)
+{
+    Form<Z> q;
+    q.a = Z(__ldg(rec + 0)); q.b = Z(__ldg(rec + 1)); q.c = Z(__ldg(rec + 2));
+    q.f = Z(__ldg(rec + 3)); q.g = Z(__ldg(rec + 4)); q.h = Z(__ldg(rec + 5));
+    return q;
+}
+template <class Z>
+__device__ __forceinline__ Iso<Z> load_iso(const i64 *m)
+{
+    Iso<Z> s;
+    s.a11 = Z(__ldg(m + 0)); s.a12 = Z(__ldg(m + 1)); s.a13 = Z(__ldg(m + 2));
+    s.a21 = Z(__ldg(m + 3)); s.a22 = Z(__ldg(m + 4)); s.a23 = Z(__ldg(m + 5));
+    s.a31 = Z(__ldg(m + 6)); s.a32 = Z(__ldg(m + 7)); s.a33 = Z(__ldg(m + 8));
+    return s;
+}
+
+// ---------------------------------------------------------------------------
+// One neighbor, start to finish: the loop body of Genus.h:567-618.
+// ---------------------------------------------------------------------------
+enum NeighborStatus { NBR_OK = 0, NBR_OVERFLOW = 1, NBR_NOT_FOUND = 2 };
+
+template <class Z>
+struct Neighbor {
+    u32 vx, vy, vz;   // isotropic line
+    Form<Z> q;        // reduced neighbor
+    Iso<Z> s;         // representative -> neighbor
+    Iso<Z> comp;      // cur.s * s * rep.sinv (valid when composed)
+    Z denom;          // p * scalar(cur) * scalar(rep) (valid when composed)
+    int r;
+    u32 spin;
+    bool composed;
+};
+
+// want_comp: also produce the composed isometry when r == n (IsometrySequence
+// has no r == n shortcut, IsometrySequence.h:63-69).
+template <class Z>
+__device__ __forceinline__ int one_neighbor(int n, u32 t, const RepPrime &rp, const PrimeCtx &pc,
+                                            const GenusCtx &gc, bool want_comp, Neighbor<Z> &o)
+{
+    const i64 *cur = gc.cur + (size_t)n * TB_REC_WORDS;
+    Form<Z> q = load_form<Z>(cur);
+    line_for_t(rp, t, pc, o.vx, o.vy, o.vz);
+    if (!build_neighbor(q, o.vx, o.vy, o.vz, __ldg(gc.disc + n), pc, o.q, o.s)) return NBR_OVERFLOW;
+    if (!eisenstein_reduce(o.q, o.s)) return NBR_OVERFLOW;
+
+    const int r = genus_lookup(o.q, gc);                     // Genus.h:575
+    if (r < 0) return NBR_NOT_FOUND;
+    o.r = r;
+    o.composed = false;
+
+    const Z pz = Z((i64)pc.p);
+    if (r != n || want_comp)                                 // Genus.h:588-615
+    {
+        const i64 *rep = gc.rep + (size_t)r * TB_REC_WORDS;
+        Iso<Z> cs = load_iso<Z>(cur + 7);
+        Iso<Z> rsinv = load_iso<Z>(rep + 7);
+        o.comp = iso_mul(iso_mul(cs, o.s), rsinv);
+        o.denom = pz * Z(__ldg(cur + 6)) * Z(__ldg(rep + 6));
+        o.composed = true;
+    }
+    if (r == n)                                              // Genus.h:582-585
+    {
+        o.spin = spinor_norm(o.q, o.s, pz, gc);
+    }
+    else
+    {
+        Form<Z> mother = load_form<Z>(gc.rep);
+        o.spin = spinor_norm(mother, o.comp, o.denom, gc);
+    }
+    return NBR_OK;
+}
+
+}  // namespace tb

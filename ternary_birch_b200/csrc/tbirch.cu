@@ -1,0 +1,902 @@
+// tbirch.cu -- libtbirch.so: the C ABI of include/tbirch.h over the sm_100a kernels.
+//
+// Host responsibilities (everything else runs on the device):
+//   * genus table import + device hash table build            Genus.h:248-303, HashMap.h:107-147
+//   * per-representative conic base points, which consume the reference's
+//     sequential std::mt19937 / std::uniform_int_distribution stream and so
+//     define the order of the p+1 lines of every representative
+//                                                             Fp.h:10-25,97-168; QuadForm.h:847-935
+//   * error translation to the reference's exception texts    NeighborManager.h:350-352, HashMap.h:77
+// There is no CPU fallback: without a CUDA device every compute call fails.
+#include "../../include/tbirch.h"
+#include "tb_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <random>
+#include <string>
+#include <vector>
+
+using namespace tb;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches(0);
+
+static int fail(tb_status st, const std::string &msg)
+{
+    g_last_error = msg;
+    return (int)st;
+}
+
+#define TB_CUDA(expr)                                                                            \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return fail(TB_ERR_RUNTIME, std::string("CUDA error: ") + cudaGetErrorString(_e) +   \
+                                            " at " #expr);                                       \
+    } while (0)
+
+static const char *MSG_OVERFLOW =
+    "An overflow has occurred. The p-neighbor's discriminant does not match the original.";
+static const char *MSG_NOT_FOUND = "Key not found.";
+static const char *MSG_BAD_PRIME = "Prime must not divide the discriminant.";
+static const char *MSG_NO_MORE = "No more isometries.";
+
+// ---------------------------------------------------------------------------
+// Host Fp with the reference's RNG (Fp.h:10-25).  Canonical residues; the
+// reference's lazy [0,kp) representation never changes a decision.
+// ---------------------------------------------------------------------------
+struct HostFp {
+    uint64_t p;
+    std::mt19937 rng;
+    std::uniform_int_distribution<> distr;
+
+    HostFp(uint64_t prime, uint64_t seed) : p(prime), rng(seed), distr(0, (int)(prime - 1)) {}
+
+    uint64_t draw() { return (uint64_t)distr(rng); }
+    uint64_t mul(uint64_t a, uint64_t b) const { return (a * b) % p; }   // a, b < p < 2^31
+    uint64_t add(uint64_t a, uint64_t b) const { uint64_t s = a + b; return s >= p ? s - p : s; }
+    uint64_t sub(uint64_t a, uint64_t b) const { return a >= b ? a - b : a + p - b; }
+    uint64_t residue(int64_t x) const
+    {
+        int64_t v = x % (int64_t)p;
+        return (uint64_t)(v < 0 ? v + (int64_t)p : v);
+    }
+    uint64_t power(uint64_t a, uint64_t e) const
+    {
+        uint64_t r = 1 % p;
+        for (; e; e >>= 1, a = mul(a, a))
+            if (e & 1) r = mul(r, a);
+        return r;
+    }
+    int legendre(uint64_t a) const
+    {
+        a %= p;
+        if (!a) return 0;
+        return power(a, (p - 1) / 2) == 1 ? 1 : -1;
+    }
+    uint64_t inverse(uint64_t a) const { return a % p ? power(a % p, p - 2) : 0; }
+
+    // Tonelli-Shanks as the reference runs it (Fp.h:97-145): the non-residue is
+    // drawn from the shared RNG, so the draws are part of the stream.
+    uint64_t square_root(uint64_t a)
+    {
+        a %= p;
+        if (a <= 1) return a;
+        if (legendre(a) != 1) return 0;
+        uint64_t odd = p - 1;
+        int twos = 0;
+        while (!(odd & 1)) { odd >>= 1; ++twos; }
+        if (twos == 1) return power(a, (p + 1) / 4);
+        uint64_t z = draw();
+        while (z == 0 || legendre(z) == 1) z = draw();
+        int m = twos;
+        uint64_t c = power(z, odd), r = power(a, (odd + 1) / 2), t = power(a, odd);
+        while (t != 1)
+        {
+            int i = 0;
+            for (uint64_t t1 = t; t1 != 1; t1 = mul(t1, t1)) ++i;
+            uint64_t b = power(c, 1ull << (m - i - 1));
+            r = mul(r, b);
+            c = mul(b, b);
+            t = mul(t, c);
+            m = i;
+        }
+        return r;
+    }
+};
+
+// One representative's base point (QuadFormFp::isotropic_vector, QuadForm.h:847-907):
+// pick a line x = r z' .. through random (r, s) until the conic meets it in a
+// rational point.  p = 2 packs the three isotropic vectors instead (915-935).
+static void base_point(HostFp &F, const int64_t *q, uint32_t out[3])
+{
+    const uint64_t p = F.p;
+    const uint64_t a = F.residue(q[0]), b = F.residue(q[1]), c = F.residue(q[2]);
+    const uint64_t f = F.residue(q[3]), g = F.residue(q[4]), h = F.residue(q[5]);
+    if (p == 2)
+    {
+        // nonzero vectors 1..7 as bits (x y z); keep the first three isotropic ones
+        uint32_t found[3] = {0, 0, 0};
+        int cnt = 0;
+        const uint64_t val[8] = {1, c, b, b ^ f ^ c, a, a ^ g ^ c, a ^ h ^ b, a ^ b ^ c ^ f ^ g ^ h};
+        for (uint32_t v = 1; v < 8; ++v)
+            if (val[v] == 0 && cnt < 3) found[cnt++] = v;
+        out[0] = found[0]; out[1] = found[1]; out[2] = found[2];
+        return;
+    }
+    for (;;)
+    {
+        uint64_t r = 0, br = 0, alpha = 0;
+        while (alpha == 0)
+        {
+            r = F.draw();
+            br = F.mul(b, r);
+            alpha = F.add(F.mul(F.add(br, h), r), a);                       // Q(1, r, 0)
+        }
+        const uint64_t s = F.draw();
+        const uint64_t beta = F.add(F.add(F.mul(F.add(F.add(br, br), h), s), F.mul(f, r)), g);
+        const uint64_t gamma = F.add(F.mul(F.add(F.mul(b, s), f), s), c);   // Q(0, s, 1)
+        uint64_t four_ag = F.mul(gamma, alpha);
+        four_ag = F.add(four_ag, four_ag);
+        four_ag = F.add(four_ag, four_ag);
+        const uint64_t disc = F.sub(F.mul(beta, beta), four_ag);
+        if (F.legendre(disc) < 0) continue;
+        const uint64_t root = F.sub(F.square_root(disc), beta);
+        const uint64_t x = F.mul(root, F.inverse(F.add(alpha, alpha)));
+        out[0] = (uint32_t)x;
+        out[1] = (uint32_t)F.add(F.mul(r, x), s);
+        out[2] = 1;
+        return;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// device buffer helper
+// ---------------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+    T *ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = std::max(n, (size_t)16);
+        cudaError_t e = cudaMalloc((void **)&ptr, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+struct PrimeState {
+    uint64_t p = 0;
+    PrimeCtx pc;
+    std::vector<uint32_t> base;   // [N][3] host copy, all representatives
+};
+
+struct tb_genus {
+    int N = 0, K = 0;
+    uint64_t seed = 0;
+    int64_t disc = 0;
+    std::vector<int64_t> primes, conductors, dims, q;
+    std::vector<int32_t> lut;
+
+    cudaStream_t stream = 0;
+    DevBuf<i64> d_cur, d_rep, d_disc;
+    DevBuf<int> d_slots, d_lut;
+    GenusCtx gc;
+
+    // per-prime state (valid for cur_p)
+    PrimeState ps;
+    DevBuf<u32> d_invlut, d_base, d_W;
+    DevBuf<RepPrime> d_rp;
+    int rp_begin = -1, rp_rows = 0;
+    DevBuf<u64> d_err;
+    u64 *h_err = nullptr;       // pinned [2]
+    uint32_t *h_base = nullptr; // pinned staging
+    size_t h_base_cap = 0;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    float last_ms_nbr = 0.f, last_ms_rows = 0.f;
+    int64_t last_neighbors = 0;
+    bool timing_valid = false;
+};
+
+struct tb_hecke {
+    tb_genus *g = nullptr;
+    int C = 0;
+    int rep_begin = 0, rep_end = 0;
+    std::vector<int> rows, rowfirst, rowbase;
+    std::vector<int64_t> nnz, nnzbase;
+    DevBuf<int> d_indptr, d_data, d_indices;
+};
+
+struct tb_isoseq {
+    tb_genus *g = nullptr;
+    uint64_t p = 0;
+    int precise = 0;
+    int64_t next_rep = 0;          // next representative to compute
+    std::vector<int64_t> chunk;    // records of the current chunk
+    size_t pos = 0;                // next record within chunk
+    int64_t delivered = 0, total = 0;
+};
+
+// ---------------------------------------------------------------------------
+// library
+// ---------------------------------------------------------------------------
+extern "C" int tb_abi_version(void) { return TBIRCH_ABI_VERSION; }
+extern "C" const char *tb_last_error(void) { return g_last_error.c_str(); }
+extern "C" uint64_t tb_launch_count(void) { return g_launches.load(); }
+
+static int require_device()
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+    {
+        cudaGetLastError();
+        return fail(TB_ERR_RUNTIME, "libtbirch: no CUDA device available (there is no CPU fallback).");
+    }
+    return TB_OK;
+}
+
+static int upload_table(tb_genus *g, const tb_genus_desc *d)
+{
+    const int N = g->N, K = g->K;
+    std::vector<i64> cur((size_t)N * TB_REC_WORDS), rep((size_t)N * TB_REC_WORDS), disc(N);
+    for (int n = 0; n < N; ++n)
+    {
+        i64 *c = &cur[(size_t)n * TB_REC_WORDS], *r = &rep[(size_t)n * TB_REC_WORDS];
+        for (int i = 0; i < 6; ++i) c[i] = r[i] = d->q[6 * n + i];
+        c[6] = r[6] = d->scalar[n];
+        for (int i = 0; i < 9; ++i) { c[7 + i] = d->s[9 * n + i]; r[7 + i] = d->sinv[9 * n + i]; }
+        // wrap-around discriminant of the representative (NeighborManager.h:16)
+        const u64 a = (u64)c[0], b = (u64)c[1], cc = (u64)c[2], f = (u64)c[3], gg = (u64)c[4], h = (u64)c[5];
+        disc[n] = (i64)(a * (4ull * b * cc - f * f) - b * gg * gg + h * (f * gg - cc * h));
+    }
+    // open-addressing table of representatives: 2 * 2^ceil(log2 N) slots (>= 32), linear probing,
+    // keyed by the reference's FNV hash of the six coefficients.
+    int lg = 4;
+    while ((1ll << lg) < N) ++lg;
+    const u32 slots = 1u << (lg + 1);
+    std::vector<int> table(slots, -1);
+    for (int n = 0; n < N; ++n)
+    {
+        u64 fnv = 0x811c9dc5ull;
+        for (int i = 0; i < 6; ++i) fnv = (fnv ^ (u64)d->q[6 * n + i]) * 0x01000193ull;
+        u32 s = (u32)fnv & (slots - 1);
+        while (table[s] != -1) s = (s + 1) & (slots - 1);
+        table[s] = n;
+    }
+    TB_CUDA(g->d_cur.reserve(cur.size()));
+    TB_CUDA(g->d_rep.reserve(rep.size()));
+    TB_CUDA(g->d_disc.reserve(N));
+    TB_CUDA(g->d_slots.reserve(slots));
+    TB_CUDA(g->d_lut.reserve((size_t)N << K));
+    TB_CUDA(cudaMemcpyAsync(g->d_cur.ptr, cur.data(), cur.size() * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
+    TB_CUDA(cudaMemcpyAsync(g->d_rep.ptr, rep.data(), rep.size() * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
+    TB_CUDA(cudaMemcpyAsync(g->d_disc.ptr, disc.data(), N * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
+    TB_CUDA(cudaMemcpyAsync(g->d_slots.ptr, table.data(), slots * sizeof(int), cudaMemcpyHostToDevice, g->stream));
+    TB_CUDA(cudaMemcpyAsync(g->d_lut.ptr, d->lut, ((size_t)N << K) * sizeof(int), cudaMemcpyHostToDevice, g->stream));
+    TB_CUDA(cudaStreamSynchronize(g->stream));
+
+    GenusCtx &gc = g->gc;
+    memset(&gc, 0, sizeof(gc));
+    gc.N = N; gc.K = K; gc.slot_mask = slots - 1;
+    gc.cur = g->d_cur.ptr; gc.rep = g->d_rep.ptr; gc.disc = g->d_disc.ptr; gc.slots = g->d_slots.ptr;
+    for (int i = 0; i < K; ++i) gc.spin[i] = make_invdiv((u64)d->primes[i]);
+    return TB_OK;
+}
+
+extern "C" int tb_genus_create(const tb_genus_desc *d, tb_genus **out)
+{
+    if (!d || !out) return fail(TB_ERR_INVALID_ARGUMENT, "tb_genus_create: null argument");
+    *out = nullptr;
+    if (int rc = require_device()) return rc;
+    if (d->K > 63) return fail(TB_ERR_DOMAIN, "Must have 63 or fewer prime divisors.");
+    if (d->N <= 0 || d->K < 0 || d->K > TB_MAX_PRIMES)
+        return fail(TB_ERR_RUNTIME, "tb_genus_create: unsupported genus shape (need 1 <= N, K <= 16)");
+    int bitsN = 0;
+    while ((1ll << bitsN) < d->N) ++bitsN;
+    if (bitsN + d->K > 31)
+        return fail(TB_ERR_RUNTIME, "tb_genus_create: N * 2^K does not fit the packed 32-bit neighbor word");
+    for (int64_t i = 0; i < d->K; ++i)
+        if (d->primes[i] < 2) return fail(TB_ERR_INVALID_ARGUMENT, "tb_genus_create: prime divisor < 2");
+
+    std::unique_ptr<tb_genus> g(new tb_genus);
+    g->N = (int)d->N; g->K = (int)d->K; g->seed = d->seed; g->disc = d->disc;
+    const int C = 1 << g->K;
+    g->primes.assign(d->primes, d->primes + g->K);
+    g->conductors.assign(d->conductors, d->conductors + C);
+    g->dims.assign(d->dims, d->dims + C);
+    g->q.assign(d->q, d->q + 6 * (size_t)g->N);
+    g->lut.assign(d->lut, d->lut + ((size_t)g->N << g->K));
+    if (int rc = upload_table(g.get(), d)) return rc;
+    TB_CUDA(g->d_err.reserve(2));
+    TB_CUDA(cudaMallocHost((void **)&g->h_err, 2 * sizeof(u64)));
+    TB_CUDA(cudaEventCreate(&g->ev0));
+    TB_CUDA(cudaEventCreate(&g->ev1));
+    TB_CUDA(cudaEventCreate(&g->ev2));
+    *out = g.release();
+    return TB_OK;
+}
+
+extern "C" int tb_genus_upload(tb_genus *g, const tb_genus_desc *d)
+{
+    if (!g || !d) return fail(TB_ERR_INVALID_ARGUMENT, "tb_genus_upload: null argument");
+    if (d->N != g->N || d->K != g->K) return fail(TB_ERR_INVALID_ARGUMENT, "tb_genus_upload: shape mismatch");
+    g->q.assign(d->q, d->q + 6 * (size_t)g->N);
+    g->lut.assign(d->lut, d->lut + ((size_t)g->N << g->K));
+    g->seed = d->seed;
+    g->ps.p = 0;
+    g->rp_begin = -1;
+    return upload_table(g, d);
+}
+
+extern "C" void tb_genus_destroy(tb_genus *g)
+{
+    if (!g) return;
+    g->d_cur.release(); g->d_rep.release(); g->d_disc.release(); g->d_slots.release(); g->d_lut.release();
+    g->d_invlut.release(); g->d_base.release(); g->d_W.release(); g->d_rp.release(); g->d_err.release();
+    if (g->h_err) cudaFreeHost(g->h_err);
+    if (g->h_base) cudaFreeHost(g->h_base);
+    if (g->ev0) cudaEventDestroy(g->ev0);
+    if (g->ev1) cudaEventDestroy(g->ev1);
+    if (g->ev2) cudaEventDestroy(g->ev2);
+    delete g;
+}
+
+extern "C" int tb_genus_set_stream(tb_genus *g, void *s)
+{
+    if (!g) return fail(TB_ERR_INVALID_ARGUMENT, "tb_genus_set_stream: null genus");
+    g->stream = (cudaStream_t)s;
+    return TB_OK;
+}
+extern "C" int64_t tb_genus_size(const tb_genus *g) { return g ? g->N : 0; }
+extern "C" int64_t tb_genus_num_conductors(const tb_genus *g) { return g ? (1ll << g->K) : 0; }
+extern "C" int64_t tb_genus_conductor(const tb_genus *g, int64_t k) { return g->conductors[k]; }
+extern "C" int64_t tb_genus_dim(const tb_genus *g, int64_t k) { return g->dims[k]; }
+
+extern "C" int tb_last_kernel_time(tb_genus *g, float *ms_nbr, float *ms_rows, int64_t *neighbors)
+{
+    if (!g || !g->timing_valid) return fail(TB_ERR_RUNTIME, "tb_last_kernel_time: no timed launch yet");
+    if (ms_nbr) *ms_nbr = g->last_ms_nbr;
+    if (ms_rows) *ms_rows = g->last_ms_rows;
+    if (neighbors) *neighbors = g->last_neighbors;
+    return TB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// per-prime setup
+// ---------------------------------------------------------------------------
+static bool divides_disc(const tb_genus *g, uint64_t p)
+{
+    // Genus.h:334,343: disc % p == 0
+    return p != 0 && (g->disc % (int64_t)p) == 0;
+}
+
+static int setup_prime(tb_genus *g, uint64_t p)
+{
+    if (p < 2 || p >= (1ull << 31))
+        return fail(TB_ERR_INVALID_ARGUMENT, "libtbirch: prime out of range (2 <= p < 2^31)");
+    if (g->ps.p == p) return TB_OK;
+    PrimeState &ps = g->ps;
+    ps.p = 0;
+    g->rp_begin = -1;
+    PrimeCtx &pc = ps.pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.p = (u32)p;
+    pc.pp = p * p;
+    pc.dp = make_invdiv(p);
+    pc.dpp = make_invdiv(p * p);
+    pc.use_lut = (p > 2 && p < (1ull << 22)) ? 1u : 0u;
+    if (pc.use_lut)
+    {
+        TB_CUDA(g->d_invlut.reserve(p));
+        pc.inv_lut = g->d_invlut.ptr;
+        inverse_lut_kernel<<<(unsigned)((p + 255) / 256), 256, 0, g->stream>>>(pc, g->d_invlut.ptr);
+        ++g_launches;
+        TB_CUDA(cudaGetLastError());
+    }
+    // base points of ALL representatives, in order, from one RNG stream
+    ps.base.resize(3 * (size_t)g->N);
+    HostFp F(p, g->seed);
+    for (int n = 0; n < g->N; ++n) base_point(F, &g->q[6 * (size_t)n], &ps.base[3 * (size_t)n]);
+    ps.p = p;
+    return TB_OK;
+}
+
+// base points for an explicit list of representatives visited in ascending
+// order by ONE Fp (Genus::_eigenvectors builds NeighborManagers only for the
+// set-cover representatives, Genus.h:457-462)
+static void base_points_for(tb_genus *g, uint64_t p, const std::vector<int> &reps, std::vector<uint32_t> &out)
+{
+    out.resize(3 * reps.size());
+    HostFp F(p, g->seed);
+    for (size_t i = 0; i < reps.size(); ++i) base_point(F, &g->q[6 * (size_t)reps[i]], &out[3 * i]);
+}
+
+static int stage_rows(tb_genus *g, const uint32_t *base, int rep_begin, int rows)
+{
+    const size_t words = 3 * (size_t)rows;
+    if (words > g->h_base_cap)
+    {
+        if (g->h_base) cudaFreeHost(g->h_base);
+        g->h_base = nullptr;
+        g->h_base_cap = 0;
+        TB_CUDA(cudaMallocHost((void **)&g->h_base, words * sizeof(uint32_t)));
+        g->h_base_cap = words;
+    }
+    memcpy(g->h_base, base, words * sizeof(uint32_t));
+    TB_CUDA(g->d_base.reserve(words));
+    TB_CUDA(g->d_rp.reserve(rows));
+    TB_CUDA(cudaMemcpyAsync(g->d_base.ptr, g->h_base, words * sizeof(uint32_t), cudaMemcpyHostToDevice, g->stream));
+    prep_reps_kernel<<<(rows + 127) / 128, 128, 0, g->stream>>>(g->gc, g->ps.pc, g->d_base.ptr, rep_begin, rows, g->d_rp.ptr);
+    ++g_launches;
+    TB_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
+static int prepare_rows(tb_genus *g, int rep_begin, int rows)
+{
+    if (g->rp_begin == rep_begin && g->rp_rows == rows) return TB_OK;
+    if (int rc = stage_rows(g, &g->ps.base[3 * (size_t)rep_begin], rep_begin, rows)) return rc;
+    g->rp_begin = rep_begin;
+    g->rp_rows = rows;
+    return TB_OK;
+}
+
+template <int MODE>
+static int launch_neighbors(tb_genus *g, int precise, int rep_begin, int rows, u32 *W, i64 *records)
+{
+    NbrLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.rep_begin = rep_begin;
+    L.rows = rows;
+    L.P1 = g->ps.pc.p + 1;
+    L.total = (u64)rows * L.P1;
+    L.dP1 = make_invdiv(L.P1);
+    L.rp = g->d_rp.ptr;
+    L.W = W;
+    L.records = records;
+    L.err = g->d_err.ptr;
+    const u64 blocks = (L.total + TB_NBR_THREADS - 1) / TB_NBR_THREADS;
+    if (blocks > 0x7fffffffull) return fail(TB_ERR_RUNTIME, "libtbirch: launch too large");
+    TB_CUDA(cudaMemsetAsync(g->d_err.ptr, 0xff, 2 * sizeof(u64), g->stream));
+    if (precise)
+        neighbors_kernel<C128, MODE><<<(unsigned)blocks, TB_NBR_THREADS, 0, g->stream>>>(g->gc, g->ps.pc, L);
+    else
+        neighbors_kernel<W64, MODE><<<(unsigned)blocks, TB_NBR_THREADS, 0, g->stream>>>(g->gc, g->ps.pc, L);
+    ++g_launches;
+    TB_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
+// The reference walks (n, t) in order and throws at the first failure; report
+// whichever failure has the smaller neighbor index.
+static int check_errors(tb_genus *g)
+{
+    const u64 ov = g->h_err[0], nf = g->h_err[1];
+    if (ov == ~0ull && nf == ~0ull) return TB_OK;
+    if (ov <= nf) return fail(TB_ERR_OVERFLOW, MSG_OVERFLOW);
+    return fail(TB_ERR_INVALID_ARGUMENT, MSG_NOT_FOUND);
+}
+
+// ---------------------------------------------------------------------------
+// Hecke matrices
+// ---------------------------------------------------------------------------
+static size_t rows_smem_bytes(int N, u32 P1)
+{
+    const size_t mw = (N + 31) / 32;
+    const size_t maxcols = std::min<size_t>(P1, N);
+    size_t b = (2 * mw + (maxcols + 1) + maxcols + 36) * 4 + (size_t)P1 * 2;
+    return (b + 15) & ~(size_t)15;
+}
+
+extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64_t rep_begin, int64_t rep_end,
+                                     tb_hecke **out)
+{
+    if (!g || !out) return fail(TB_ERR_INVALID_ARGUMENT, "tb_hecke_compute: null argument");
+    *out = nullptr;
+    if (divides_disc(g, p)) return fail(TB_ERR_INVALID_ARGUMENT, MSG_BAD_PRIME);
+    if (rep_begin < 0 || rep_end > g->N || rep_begin > rep_end)
+        return fail(TB_ERR_INVALID_ARGUMENT, "tb_hecke_compute_rows: bad representative range");
+    if (int rc = setup_prime(g, p)) return rc;
+
+    const int N = g->N, K = g->K, C = 1 << K;
+    const int rb = (int)rep_begin, rows = (int)(rep_end - rep_begin);
+    const u32 P1 = (u32)p + 1;
+
+    std::unique_ptr<tb_hecke> h(new tb_hecke);
+    h->g = g; h->C = C; h->rep_begin = rb; h->rep_end = (int)rep_end;
+    h->rows.assign(C, 0); h->rowfirst.assign(C, 0); h->rowbase.assign(C, 0);
+    h->nnz.assign(C, 0); h->nnzbase.assign(C, 0);
+    int total_ptr = 0;
+    for (int k = 0; k < C; ++k)
+    {
+        const int32_t *lut = &g->lut[(size_t)k * N];
+        int cnt = 0, first = -1;
+        for (int n = rb; n < (int)rep_end; ++n)
+            if (lut[n] != -1) { if (first < 0) first = lut[n]; ++cnt; }
+        h->rows[k] = cnt;
+        h->rowfirst[k] = first < 0 ? 0 : first;
+        h->rowbase[k] = total_ptr;
+        total_ptr += cnt + 1;
+    }
+    TB_CUDA(h->d_indptr.reserve(total_ptr));
+    TB_CUDA(cudaMemsetAsync(h->d_indptr.ptr, 0, (size_t)total_ptr * sizeof(int), g->stream));
+    if (rows == 0)
+    {
+        TB_CUDA(cudaStreamSynchronize(g->stream));
+        *out = h.release();
+        return TB_OK;
+    }
+
+    if (int rc = prepare_rows(g, rb, rows)) return rc;
+    TB_CUDA(g->d_W.reserve((size_t)rows * P1));
+
+    // small device-side tables for the row kernels
+    DevBuf<int> d_tab;      // rowbase | rowfirst | rowcount
+    DevBuf<i64> d_nnz;      // nnz | nnzbase
+    TB_CUDA(d_tab.reserve(3 * (size_t)C));
+    TB_CUDA(d_nnz.reserve(2 * (size_t)C));
+    std::vector<int> tab(3 * (size_t)C);
+    for (int k = 0; k < C; ++k) { tab[k] = h->rowbase[k]; tab[C + k] = h->rowfirst[k]; tab[2 * C + k] = h->rows[k]; }
+    TB_CUDA(cudaMemcpyAsync(d_tab.ptr, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, g->stream));
+
+    TB_CUDA(cudaEventRecord(g->ev0, g->stream));
+    if (int rc = launch_neighbors<MODE_PACKED>(g, precise, rb, rows, g->d_W.ptr, nullptr)) { d_tab.release(); d_nnz.release(); return rc; }
+    TB_CUDA(cudaEventRecord(g->ev1, g->stream));
+
+    RowLaunch R;
+    memset(&R, 0, sizeof(R));
+    R.N = N; R.K = K; R.rep_begin = rb; R.rows = rows; R.P1 = P1; R.mask_words = (N + 31) / 32;
+    R.W = g->d_W.ptr; R.lut = g->d_lut.ptr;
+    R.rowbase = d_tab.ptr; R.rowfirst = d_tab.ptr + C;
+    R.indptr_all = h->d_indptr.ptr;
+    R.nnzbase = d_nnz.ptr + C;
+    const size_t smem = rows_smem_bytes(N, P1);
+    if (smem > 227 * 1024)
+    {
+        d_tab.release(); d_nnz.release();
+        return fail(TB_ERR_RUNTIME, "libtbirch: row accumulation needs more shared memory than one SM has for this (N, p)");
+    }
+    int threads = (int)std::min<u32>(512, std::max<u32>(64, (P1 + 31) / 32 * 32));
+    TB_CUDA(cudaFuncSetAttribute(rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TB_CUDA(cudaFuncSetAttribute(rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rows_kernel<false><<<rows, threads, smem, g->stream>>>(R);
+    ++g_launches;
+    TB_CUDA(cudaGetLastError());
+    indptr_scan_kernel<<<C, 256, 0, g->stream>>>(h->d_indptr.ptr, d_tab.ptr, d_tab.ptr + 2 * C, d_nnz.ptr);
+    ++g_launches;
+    TB_CUDA(cudaGetLastError());
+
+    TB_CUDA(cudaMemcpyAsync(g->h_err, g->d_err.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, g->stream));
+    TB_CUDA(cudaMemcpyAsync(h->nnz.data(), d_nnz.ptr, C * sizeof(i64), cudaMemcpyDeviceToHost, g->stream));
+    TB_CUDA(cudaStreamSynchronize(g->stream));
+    if (int rc = check_errors(g)) { d_tab.release(); d_nnz.release(); return rc; }
+
+    int64_t total_nnz = 0;
+    for (int k = 0; k < C; ++k) { h->nnzbase[k] = total_nnz; total_nnz += h->nnz[k]; }
+    TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(total_nnz, 1)));
+    TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(total_nnz, 1)));
+    TB_CUDA(cudaMemcpyAsync(d_nnz.ptr + C, h->nnzbase.data(), C * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
+    R.data = h->d_data.ptr; R.indices = h->d_indices.ptr;
+    rows_kernel<true><<<rows, threads, smem, g->stream>>>(R);
+    ++g_launches;
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaEventRecord(g->ev2, g->stream));
+    TB_CUDA(cudaStreamSynchronize(g->stream));
+    cudaEventElapsedTime(&g->last_ms_nbr, g->ev0, g->ev1);
+    cudaEventElapsedTime(&g->last_ms_rows, g->ev1, g->ev2);
+    g->last_neighbors = (int64_t)rows * P1;
+    g->timing_valid = true;
+    d_tab.release(); d_nnz.release();
+    *out = h.release();
+    return TB_OK;
+}
+
+extern "C" int tb_hecke_compute(tb_genus *g, uint64_t p, int precise, tb_hecke **out)
+{
+    if (!g) return fail(TB_ERR_INVALID_ARGUMENT, "tb_hecke_compute: null genus");
+    return tb_hecke_compute_rows(g, p, precise, 0, g->N, out);
+}
+
+extern "C" int64_t tb_hecke_num_conductors(const tb_hecke *h) { return h ? h->C : 0; }
+extern "C" int64_t tb_hecke_conductor(const tb_hecke *h, int64_t k) { return h->g->conductors[k]; }
+extern "C" int64_t tb_hecke_dim(const tb_hecke *h, int64_t k) { return h->g->dims[k]; }
+extern "C" int64_t tb_hecke_rows(const tb_hecke *h, int64_t k) { return h->rows[k]; }
+extern "C" int64_t tb_hecke_row_begin(const tb_hecke *h, int64_t k) { return h->rowfirst[k]; }
+extern "C" int64_t tb_hecke_nnz(const tb_hecke *h, int64_t k) { return h->nnz[k]; }
+
+extern "C" int tb_hecke_copy_sparse(tb_hecke *h, int64_t k, int32_t *data, int32_t *indices, int32_t *indptr)
+{
+    if (!h || k < 0 || k >= h->C) return fail(TB_ERR_INVALID_ARGUMENT, "tb_hecke_copy_sparse: bad conductor index");
+    cudaStream_t st = h->g->stream;
+    const size_t nnz = (size_t)h->nnz[k];
+    if (nnz && data) TB_CUDA(cudaMemcpyAsync(data, h->d_data.ptr + h->nnzbase[k], nnz * sizeof(int), cudaMemcpyDefault, st));
+    if (nnz && indices) TB_CUDA(cudaMemcpyAsync(indices, h->d_indices.ptr + h->nnzbase[k], nnz * sizeof(int), cudaMemcpyDefault, st));
+    if (indptr) TB_CUDA(cudaMemcpyAsync(indptr, h->d_indptr.ptr + h->rowbase[k], ((size_t)h->rows[k] + 1) * sizeof(int), cudaMemcpyDefault, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    return TB_OK;
+}
+
+extern "C" int tb_hecke_copy_dense(tb_hecke *h, int64_t k, int32_t *matrix)
+{
+    if (!h || k < 0 || k >= h->C) return fail(TB_ERR_INVALID_ARGUMENT, "tb_hecke_copy_dense: bad conductor index");
+    cudaStream_t st = h->g->stream;
+    const int rows = h->rows[k];
+    const int dim = (int)h->g->dims[k];
+    const size_t cells = (size_t)rows * dim;
+    if (cells == 0) return TB_OK;
+    cudaPointerAttributes attr;
+    bool on_device = cudaPointerGetAttributes(&attr, matrix) == cudaSuccess &&
+                     (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    DevBuf<int> tmp;
+    int *dst = matrix;
+    if (!on_device)
+    {
+        TB_CUDA(tmp.reserve(cells));
+        dst = tmp.ptr;
+    }
+    TB_CUDA(cudaMemsetAsync(dst, 0, cells * sizeof(int), st));
+    if (h->nnz[k])
+    {
+        dense_scatter_kernel<<<rows, 128, 0, st>>>(h->d_indptr.ptr + h->rowbase[k], h->d_data.ptr + h->nnzbase[k],
+                                                   h->d_indices.ptr + h->nnzbase[k], rows, dim, dst);
+        ++g_launches;
+        TB_CUDA(cudaGetLastError());
+    }
+    if (!on_device) TB_CUDA(cudaMemcpyAsync(matrix, dst, cells * sizeof(int), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    tmp.release();
+    return TB_OK;
+}
+
+extern "C" void tb_hecke_destroy(tb_hecke *h)
+{
+    if (!h) return;
+    h->d_indptr.release(); h->d_data.release(); h->d_indices.release();
+    delete h;
+}
+
+// ---------------------------------------------------------------------------
+// per-neighbor records (parity tests)
+// ---------------------------------------------------------------------------
+extern "C" int tb_neighbor_records(tb_genus *g, uint64_t p, int precise, int64_t rep_begin, int64_t rep_end,
+                                   int64_t *records)
+{
+    if (!g || !records) return fail(TB_ERR_INVALID_ARGUMENT, "tb_neighbor_records: null argument");
+    if (divides_disc(g, p)) return fail(TB_ERR_INVALID_ARGUMENT, MSG_BAD_PRIME);
+    if (rep_begin < 0 || rep_end > g->N || rep_begin >= rep_end)
+        return fail(TB_ERR_INVALID_ARGUMENT, "tb_neighbor_records: bad representative range");
+    if (int rc = setup_prime(g, p)) return rc;
+    const int rows = (int)(rep_end - rep_begin);
+    const size_t words = (size_t)rows * (p + 1) * 20;
+    if (int rc = prepare_rows(g, (int)rep_begin, rows)) return rc;
+    DevBuf<i64> d_rec;
+    TB_CUDA(d_rec.reserve(words));
+    TB_CUDA(cudaMemsetAsync(d_rec.ptr, 0, words * sizeof(i64), g->stream));
+    if (int rc = launch_neighbors<MODE_RECORDS>(g, precise, (int)rep_begin, rows, nullptr, d_rec.ptr)) { d_rec.release(); return rc; }
+    TB_CUDA(cudaMemcpyAsync(g->h_err, g->d_err.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, g->stream));
+    TB_CUDA(cudaMemcpyAsync(records, d_rec.ptr, words * sizeof(i64), cudaMemcpyDefault, g->stream));
+    TB_CUDA(cudaStreamSynchronize(g->stream));
+    d_rec.release();
+    return check_errors(g);
+}
+
+// ---------------------------------------------------------------------------
+// eigenvalues
+// ---------------------------------------------------------------------------
+extern "C" int tb_eigenvalues(tb_genus *g, uint64_t p, int precise, int64_t V, const int32_t *vecs,
+                              const int64_t *cond_mask, const int64_t *rep_index, int32_t *out)
+{
+    if (!g || (V > 0 && (!vecs || !cond_mask || !rep_index || !out)))
+        return fail(TB_ERR_INVALID_ARGUMENT, "tb_eigenvalues: null argument");
+    if (V == 0) return TB_OK;
+    if (divides_disc(g, p)) return fail(TB_ERR_INVALID_ARGUMENT, MSG_BAD_PRIME);
+    const int N = g->N;
+    for (int64_t v = 0; v < V; ++v)
+        if (rep_index[v] < 0 || rep_index[v] >= N) return fail(TB_ERR_INVALID_ARGUMENT, "tb_eigenvalues: bad representative index");
+    if (int rc = setup_prime(g, p)) return rc;
+    const u32 P1 = (u32)p + 1;
+
+    // distinct representatives, ascending (EigenvectorManager::indices is sorted, Eigenvector.h:160-161)
+    std::vector<int> reps;
+    for (int64_t v = 0; v < V; ++v) reps.push_back((int)rep_index[v]);
+    std::sort(reps.begin(), reps.end());
+    reps.erase(std::unique(reps.begin(), reps.end()), reps.end());
+    std::vector<uint32_t> base;
+    base_points_for(g, p, reps, base);
+
+    DevBuf<int> d_vecs, d_sel, d_out;
+    DevBuf<i64> d_cond;
+    auto cleanup = [&]() { d_vecs.release(); d_sel.release(); d_out.release(); d_cond.release(); };
+    TB_CUDA(d_vecs.reserve((size_t)V * N));
+    TB_CUDA(d_cond.reserve(V));
+    TB_CUDA(d_sel.reserve(V));
+    TB_CUDA(d_out.reserve(V));
+    TB_CUDA(cudaMemcpyAsync(d_vecs.ptr, vecs, (size_t)V * N * sizeof(int), cudaMemcpyDefault, g->stream));
+    TB_CUDA(cudaMemcpyAsync(d_cond.ptr, cond_mask, V * sizeof(i64), cudaMemcpyDefault, g->stream));
+    TB_CUDA(cudaMemsetAsync(d_out.ptr, 0, V * sizeof(int), g->stream));
+    TB_CUDA(g->d_W.reserve(P1));
+
+    std::vector<int> host_vecs_at_rep(V);
+    for (size_t i = 0; i < reps.size(); ++i)
+    {
+        const int n = reps[i];
+        std::vector<int> sel;
+        for (int64_t v = 0; v < V; ++v) if (rep_index[v] == n) sel.push_back((int)v);
+        g->rp_begin = -1;   // the staged rows below are not the Hecke shard's
+        if (int rc = stage_rows(g, &base[3 * i], n, 1)) { cleanup(); return rc; }
+        if (int rc = launch_neighbors<MODE_PACKED>(g, precise, n, 1, g->d_W.ptr, nullptr)) { cleanup(); return rc; }
+        TB_CUDA(cudaMemcpyAsync(g->h_err, g->d_err.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, g->stream));
+        TB_CUDA(cudaMemcpyAsync(d_sel.ptr, sel.data(), sel.size() * sizeof(int), cudaMemcpyHostToDevice, g->stream));
+        TB_CUDA(cudaStreamSynchronize(g->stream));
+        if (int rc = check_errors(g)) { cleanup(); return rc; }
+        eigen_dot_kernel<<<(P1 + 255) / 256, 256, 0, g->stream>>>(g->d_W.ptr, P1, g->K, N, d_vecs.ptr, d_cond.ptr,
+                                                                  d_sel.ptr, (int)sel.size(), d_out.ptr);
+        ++g_launches;
+        TB_CUDA(cudaGetLastError());
+        TB_CUDA(cudaStreamSynchronize(g->stream));
+    }
+    std::vector<int> sums(V);
+    TB_CUDA(cudaMemcpy(sums.data(), d_out.ptr, V * sizeof(int), cudaMemcpyDeviceToHost));
+    cleanup();
+    // host copy of the pivot coordinates for the final exact division (Genus.h:504-510)
+    std::vector<int> pivot(V);
+    cudaPointerAttributes attr;
+    bool vecs_on_device = cudaPointerGetAttributes(&attr, vecs) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    for (int64_t v = 0; v < V; ++v)
+    {
+        if (vecs_on_device)
+            TB_CUDA(cudaMemcpy(&pivot[v], vecs + (size_t)v * N + rep_index[v], sizeof(int), cudaMemcpyDeviceToHost));
+        else
+            pivot[v] = vecs[(size_t)v * N + rep_index[v]];
+        if (pivot[v] == 0) return fail(TB_ERR_INVALID_ARGUMENT, "tb_eigenvalues: eigenvector vanishes at its representative");
+        out[v] = sums[v] / pivot[v];
+    }
+    return TB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// isometry sequence
+// ---------------------------------------------------------------------------
+extern "C" int tb_isoseq_open(tb_genus *g, uint64_t p, int precise, tb_isoseq **out)
+{
+    if (!g || !out) return fail(TB_ERR_INVALID_ARGUMENT, "tb_isoseq_open: null argument");
+    *out = nullptr;
+    if (int rc = setup_prime(g, p)) return rc;
+    tb_isoseq *it = new tb_isoseq;
+    it->g = g; it->p = p; it->precise = precise;
+    it->total = (int64_t)g->N * (int64_t)(p + 1);
+    *out = it;
+    return TB_OK;
+}
+
+extern "C" int tb_isoseq_done(const tb_isoseq *it) { return !it || it->delivered >= it->total; }
+
+static int isoseq_fill(tb_isoseq *it)
+{
+    tb_genus *g = it->g;
+    if (int rc = setup_prime(g, it->p)) return rc;
+    const int64_t P1 = (int64_t)it->p + 1;
+    const int64_t max_records = 1 << 20;
+    int rows = (int)std::max<int64_t>(1, std::min<int64_t>(g->N - it->next_rep, max_records / P1));
+    const size_t words = (size_t)rows * P1 * 12;
+    if (int rc = prepare_rows(g, (int)it->next_rep, rows)) return rc;
+    DevBuf<i64> d_rec;
+    TB_CUDA(d_rec.reserve(words));
+    if (int rc = launch_neighbors<MODE_ISOSEQ>(g, it->precise, (int)it->next_rep, rows, nullptr, d_rec.ptr)) { d_rec.release(); return rc; }
+    it->chunk.resize(words);
+    TB_CUDA(cudaMemcpyAsync(g->h_err, g->d_err.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, g->stream));
+    TB_CUDA(cudaMemcpyAsync(it->chunk.data(), d_rec.ptr, words * sizeof(i64), cudaMemcpyDeviceToHost, g->stream));
+    TB_CUDA(cudaStreamSynchronize(g->stream));
+    d_rec.release();
+    if (int rc = check_errors(g)) return rc;
+    it->next_rep += rows;
+    it->pos = 0;
+    return TB_OK;
+}
+
+extern "C" int tb_isoseq_read(tb_isoseq *it, int64_t max_records, int64_t *records, int64_t *got)
+{
+    if (!it || !records || !got) return fail(TB_ERR_INVALID_ARGUMENT, "tb_isoseq_read: null argument");
+    *got = 0;
+    while (*got < max_records && it->delivered < it->total)
+    {
+        if (it->pos * 12 >= it->chunk.size())
+            if (int rc = isoseq_fill(it)) return rc;
+        const int64_t avail = (int64_t)(it->chunk.size() / 12 - it->pos);
+        const int64_t take = std::min<int64_t>(avail, max_records - *got);
+        memcpy(records + 12 * *got, &it->chunk[12 * it->pos], (size_t)take * 12 * sizeof(int64_t));
+        it->pos += take;
+        it->delivered += take;
+        *got += take;
+    }
+    return TB_OK;
+}
+
+extern "C" int tb_isoseq_next(tb_isoseq *it, int64_t isometry[9], int64_t *denominator, int64_t *src, int64_t *dst)
+{
+    if (!it) return fail(TB_ERR_INVALID_ARGUMENT, "tb_isoseq_next: null iterator");
+    if (tb_isoseq_done(it)) return fail(TB_ERR_DOMAIN, MSG_NO_MORE);
+    int64_t rec[12], got = 0;
+    if (int rc = tb_isoseq_read(it, 1, rec, &got)) return rc;
+    memcpy(isometry, rec, 9 * sizeof(int64_t));
+    if (denominator) *denominator = rec[9];
+    if (src) *src = rec[10];
+    if (dst) *dst = rec[11];
+    return TB_OK;
+}
+
+extern "C" void tb_isoseq_close(tb_isoseq *it) { delete it; }
+
+// ---------------------------------------------------------------------------
+// integer-pipe microbenchmark
+// ---------------------------------------------------------------------------
+template <int KIND>
+static int peak_one(double ops_per_iter_per_thread, double *out)
+{
+    int dev = 0, sms = 0;
+    TB_CUDA(cudaGetDevice(&dev));
+    TB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    u32 *sink = nullptr;
+    TB_CUDA(cudaMalloc((void **)&sink, 4));
+    cudaEvent_t e0, e1;
+    TB_CUDA(cudaEventCreate(&e0));
+    TB_CUDA(cudaEventCreate(&e1));
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    int_peak_kernel<KIND><<<blocks, threads>>>(sink, 64, 12345u);   // warm-up
+    TB_CUDA(cudaDeviceSynchronize());
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep)
+    {
+        TB_CUDA(cudaEventRecord(e0));
+        int_peak_kernel<KIND><<<blocks, threads>>>(sink, iters, 12345u + rep);
+        TB_CUDA(cudaEventRecord(e1));
+        TB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double ops = (double)blocks * threads * iters * ops_per_iter_per_thread;
+        best = std::max(best, ops / (ms * 1e-3));
+        g_launches += 1;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *out = best;
+    return TB_OK;
+}
+
+extern "C" int tb_int_peak(double *imad, double *iadd, double *mixed)
+{
+    if (int rc = require_device()) return rc;
+    double a = 0, b = 0, c = 0;
+    // per inner iteration: 16 unrolled steps x 8 chains; KIND 0: 1 IMAD each; KIND 1: 2 logic/add ops each; KIND 2: both
+    if (int rc = peak_one<0>(16.0 * 8.0, &a)) return rc;
+    if (int rc = peak_one<1>(16.0 * 8.0 * 2.0, &b)) return rc;
+    if (int rc = peak_one<2>(16.0 * 8.0 * 3.0, &c)) return rc;
+    if (imad) *imad = a;
+    if (iadd) *iadd = b;
+    if (mixed) *mixed = c;
+    return TB_OK;
+}

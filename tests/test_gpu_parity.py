@@ -1,0 +1,190 @@
+"""GPU: the CUDA path, called through the C ABI, against the oracle port, the committed
+golden vectors from the unmodified reference and (when oracle/_ref travelled) the
+reference binary itself.  Integer work: every comparison is bit-exact."""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import csr_digest, primes_upto
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def genus(tables):
+    from ternary_birch_b200 import Genus
+    cache = {}
+
+    def get(name, precise):
+        key = (name, precise)
+        if key not in cache:
+            cache[key] = Genus(tables(name), precise=precise)
+        return cache[key]
+    yield get
+    for g in cache.values():
+        g.close()
+
+
+def assert_same_csr(got: dict, want: list, tag=""):
+    assert sorted(got) == sorted(m["conductor"] for m in want)
+    for m in want:
+        data, indices, indptr = got[m["conductor"]]
+        assert np.array_equal(indptr, m["indptr"]), (tag, m["conductor"], "indptr")
+        assert np.array_equal(indices, m["indices"]), (tag, m["conductor"], "indices")
+        assert np.array_equal(data, m["data"]), (tag, m["conductor"], "data")
+
+
+def test_c1_every_entry(genus, hecke_small):
+    """Config 1: BirchGenus(11), T_p for all p < 100, all conductors, every matrix entry."""
+    for precise in (False, True):
+        g = genus("11", precise)
+        for p in primes_upto(100):
+            if p == 11:
+                continue
+            got = g.hecke_matrix_sparse(p)
+            for k, cond in enumerate((1, 11)):
+                tag = f"L11_p{p}_{'z' if precise else 'z64'}_k{k}"
+                data, indices, indptr = got[cond]
+                assert np.array_equal(data, hecke_small[tag + "_data"]), tag
+                assert np.array_equal(indices, hecke_small[tag + "_indices"]), tag
+                assert np.array_equal(indptr, hecke_small[tag + "_indptr"]), tag
+
+
+def test_even_level(genus, hecke_small):
+    g = genus("210_s7", False)
+    for p in (11, 13, 59):
+        got = g.hecke_matrix_sparse(p)
+        for k, cond in enumerate(g.table.conductors):
+            tag = f"L210_p{p}_z64_k{k}"
+            data, indices, indptr = got[int(cond)]
+            assert np.array_equal(data, hecke_small[tag + "_data"]), tag
+            assert np.array_equal(indices, hecke_small[tag + "_indices"]), tag
+            assert np.array_equal(indptr, hecke_small[tag + "_indptr"]), tag
+
+
+@pytest.mark.parametrize("name,p,precise", [
+    ("85085", 2, False), ("85085", 2, True), ("85085", 3, False), ("85085", 19, True),
+    ("85085", 101, False), ("85085", 101, True), ("85085", 997, False),
+    ("1062347", 2, False), ("1062347", 3, True), ("1062347", 101, False), ("1062347", 101, True),
+    ("1009091", 2, False), ("1009091", 107, False),
+])
+def test_hecke_vs_oracle_and_golden(genus, port_oracle, hecke_digests, name, p, precise):
+    """Configs 2-4 (sampled primes): every CSR array equals the oracle's, and its digest equals
+    the digest of the unmodified reference's output."""
+    got = genus(name, precise).hecke_matrix_sparse(p)
+    want = port_oracle(name).hecke(p, precise)
+    assert_same_csr(got, want, (name, p, precise))
+    key = f"L{name}_p{p}_{'z' if precise else 'z64'}"
+    if key in hecke_digests:
+        t = genus(name, precise).table
+        dig = [csr_digest(c, d, *got[int(c)]) for c, d in zip(t.conductors, t.dims)]
+        assert dig == hecke_digests[key]
+
+
+def test_c2_named_call(genus, port_oracle):
+    """Config 2: hecke_matrix(101, 17*19) plus all conductors, int64 and precise, sparse and dense."""
+    want = {m["conductor"]: m for m in port_oracle("1062347").hecke(101, False, sparse=False)}
+    for precise in (False, True):
+        g = genus("1062347", precise)
+        dense = g.hecke_matrix_dense(101)
+        assert sorted(dense) == sorted(want)
+        for cond, m in dense.items():
+            assert m.shape == (want[cond]["dim"], want[cond]["dim"])
+            assert np.array_equal(m, want[cond]["matrix"]), (precise, cond)
+        assert dense[17 * 19].shape[0] == g.dimension_map()[17 * 19]
+        # conductor-1 rows sum to p + 1
+        assert (dense[1].sum(axis=1) == 102).all()
+
+
+def test_neighbor_records(genus, records_small):
+    """Per-neighbor parity: line, reduced form, isometry, class index, spinor value."""
+    for key, want in records_small.items():
+        level, p, mode, kind = key.split("_")
+        if kind != "rec":
+            continue
+        name = {"L11": "11", "L210": "210_s7", "L85085": "85085"}[level]
+        got = genus(name, mode == "z").neighbor_records(int(p[1:]))
+        assert np.array_equal(got, want), key
+
+
+def test_neighbor_records_vs_oracle_midsize(genus, port_oracle):
+    for precise in (False, True):
+        got = genus("1062347", precise).neighbor_records(101, 100, 164)
+        want = port_oracle("1062347").neighbor_records(101, precise)[100:164]
+        assert np.array_equal(got, want)
+
+
+def test_isometry_sequence(genus, records_small):
+    from ternary_birch_b200 import IsometrySequence
+    for key, want in records_small.items():
+        level, p, mode, kind = key.split("_")
+        if kind != "iso":
+            continue
+        name = {"L11": "11", "L210": "210_s7", "L85085": "85085"}[level]
+        seq = IsometrySequence(genus(name, mode == "z"), int(p[1:]))
+        first = seq.next()
+        assert first["isometry"].ravel().tolist() == want[0][:9].tolist()
+        rest = seq.read(len(want))
+        assert np.array_equal(rest, want[1:]), key
+        assert seq.done()
+        with pytest.raises(ValueError, match="No more isometries."):
+            seq.next()
+        seq.close()
+
+
+def test_eigenvalues_c3(tables, golden_dir):
+    """Config 3: rational eigenvectors of level 5*7*11*13*17, compute_eigenvalues_upto(1000)."""
+    from ternary_birch_b200 import BirchGenus
+    gold = json.load(open(golden_dir / "eigen_85085.json"))
+    for precise, key in ((False, "aps_z64"), (True, "aps_z")):
+        b = BirchGenus(tables("85085"))
+        for v in gold["vectors"]:
+            b.add_eigenvector(v)
+        b.compute_eigenvalues_upto(1000, precise=precise)
+        for p in gold["primes"]:
+            got = [vec["aps"][p] for vec in b.eigenvectors]
+            assert got == gold[key][str(p)], (precise, p)
+    b = BirchGenus(tables("85085"))
+    for v in gold["vectors"]:
+        b.add_eigenvector(v)
+    for p in (65521, 65537, 99991):
+        assert b.compute_eigenvalues(p, precise=True) == gold["aps_z_big"][str(p)]
+
+
+def test_eigenvalues_11a(tables, golden_dir):
+    from ternary_birch_b200 import BirchGenus
+    gold = json.load(open(golden_dir / "eigen_11.json"))
+    b = BirchGenus(tables("11"))
+    for v in gold["vectors"]:
+        b.add_eigenvector(v)
+    for p, want in gold["aps_z"].items():
+        assert b.compute_eigenvalues(int(p), precise=True) == want, p
+
+
+def test_errors(genus):
+    g = genus("11", False)
+    with pytest.raises(ValueError, match="Prime must not divide the discriminant."):
+        g.hecke_matrix_sparse(11)
+    with pytest.raises(ValueError, match="Invalid conductor."):
+        g.eigenvector([1, 1], 7)
+    with pytest.raises(ValueError, match="Eigenvector has incorrect dimension."):
+        g.eigenvector([1, 1, 1], 1)
+
+
+def test_row_shards_concatenate(genus):
+    """Rows computed in shards (the multi-GPU partition) concatenate to the full matrix."""
+    g = genus("85085", False)
+    full = g.hecke_matrix_sparse(101)
+    cuts = [0, 17, 64, 65, 130]
+    parts = [g.hecke_matrix_sparse(101, a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+    for cond, (data, indices, indptr) in full.items():
+        d = np.concatenate([pt[cond][0] for pt in parts])
+        i = np.concatenate([pt[cond][1] for pt in parts])
+        ptr = [np.zeros(1, dtype=np.int64)]
+        off = 0
+        for pt in parts:
+            ptr.append(pt[cond][2][1:].astype(np.int64) + off)
+            off += int(pt[cond][2][-1])
+        assert np.array_equal(d, data) and np.array_equal(i, indices)
+        assert np.array_equal(np.concatenate(ptr), indptr)
