@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- neighbors/sec of the p-neighbor Hecke hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path
+
+Workload ("C4", BASELINE.json configs[3], the configuration the 1/2/4/8-GPU metric is
+quoted on): the genus of level 97*101*103 = 1009091 (N = 10316 representatives, K = 3,
+8 conductors, seed 1; committed fixture tests/golden/genus_1009091.npz) and T_p for a
+prime just below 10^4, int64 mode, CSR output for all conductors.  One STEP is one
+T_p: (p+1) * N neighbors enumerated, built, Eisenstein-reduced, looked up in the genus
+hash table, given their spinor character and accumulated into Hecke rows.  Under
+torchrun rank i takes the i-th largest prime below 10^4 (weak scaling: one T_p per
+rank per step, no data-path collective; a final integer gather of the rows to rank 0
+runs once after the timed region).
+
+One JSON line is printed by rank 0.  `value` has the genus table resident in HBM;
+`e2e` re-sends the table and the per-prime inputs host->device every step and reads
+every CSR array back to pinned host memory.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+LEVEL = 1009091
+TABLE = ROOT / "tests" / "golden" / f"genus_{LEVEL}.npz"
+PRIMES_DESC = [9973, 9967, 9949, 9941, 9931, 9929, 9923, 9907]   # largest primes below 10^4
+REF_SAMPLE_PRIMES = [1009, 1013, 1019, 1021, 1031, 1033, 1039, 1049, 1051, 1061, 1063, 1069, 1087, 1091, 1093, 1097,
+                     1103, 1109, 1117, 1123, 1129, 1151, 1153, 1163, 1171, 1181, 1187, 1193, 1201, 1213, 1217, 1223,
+                     1229, 1231, 1237, 1249, 1259, 1277, 1279, 1283, 1289, 1291, 1297, 1301, 1303, 1307, 1319, 1321,
+                     1327, 1361, 1367, 1373, 1381, 1399, 1409, 1423, 1427, 1429, 1433, 1439, 1447, 1451, 1453, 1459]
+METRIC = "neighbors_per_sec"
+UNIT = "neighbors/s"
+
+
+def workload_name(p):
+    return (f"C4: genus of level 97*101*103=1009091 (N=10316, K=3, seed 1), T_p all 8 conductors, "
+            f"p={p} (rank i: i-th largest prime < 10^4), int64, CSR")
+
+
+def mean_reduce_iters(p: int) -> float:
+    # measured 4.86 / 7.04 / 9.33 / 9.99 at p = 101 / 997 / 10007 / 65521
+    return 0.6 * math.log2(p) + 1.0
+
+
+def int32_ops_per_neighbor(p: int, K: int) -> float:
+    """algorithmic work per neighbor in 32-bit integer instructions."""
+    it = mean_reduce_iters(p)
+    mul64 = 101 + 12 * it
+    add64 = 107 + 87 * it + 4 * (1 << K)
+    div64 = 10 + K + 0.33 * it
+    return 4 * mul64 + 2 * add64 + 20 * div64 + 70
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, cell in zip(names, r[5:9]):
+                if cell.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None),
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------
+# the reference's CPU path (oracle/_ref = unmodified reference sources compiled here)
+# ---------------------------------------------------------------------------
+def reference_sample(primes, precise=False, timeout=1200):
+    """One OS process per prime (the reference's own parallel model,
+    scripts/generate_eigenvalues.py:205), each timing Genus::hecke_matrix_sparse(p) on
+    the workload's genus.  Returns (total neighbors, wall seconds of the slowest call, kind)."""
+    from oracle import pyoracle          # the cpu_baseline / --impl reference leg may execute oracle/
+    if pyoracle.RefBinary.available():
+        kind = "reference"
+        mode = "z" if precise else "z64"
+        procs = [subprocess.Popen([str(pyoracle.REF_BIN), "--level", str(LEVEL), "--seed", "1", "time", str(p),
+                                   mode, "sparse", "1"], stdout=subprocess.PIPE, text=True) for p in primes]
+        total, slowest = 0, 0.0
+        for pr in procs:
+            out, _ = pr.communicate(timeout=timeout)
+            rec = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+            total += rec["neighbors"]
+            slowest = max(slowest, rec["seconds"])
+        return total, slowest, kind
+    # oracle/_ref did not travel: time the plain-C port instead, one process per prime
+    kind = "port"
+    code = ("import sys,time;sys.path.insert(0,%r);import numpy as np;"
+            "from oracle.pyoracle import PortOracle,load_genus;from ternary_birch_b200 import load_genus_table;"
+            "from oracle.pyoracle import GenusArrays as G;t=load_genus_table(%r);"
+            "o=PortOracle(G(t.N,t.K,t.seed,t.disc,t.primes,t.conductors,t.dims,t.q,t.s,t.sinv,t.scalar,t.parent,t.p,t.num_auts,t.lut));"
+            "p=int(sys.argv[1]);t0=time.perf_counter();o.hecke(p,%s);print(t.N*(p+1),time.perf_counter()-t0)"
+            % (str(ROOT), str(TABLE), "True" if precise else "False"))
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(p)], stdout=subprocess.PIPE, text=True) for p in primes]
+    total, slowest = 0, 0.0
+    for pr in procs:
+        out, _ = pr.communicate(timeout=timeout)
+        n, s = out.split()[-2:]
+        total += int(n)
+        slowest = max(slowest, float(s))
+    return total, slowest, kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    primes = REF_SAMPLE_PRIMES[:min(cores, len(REF_SAMPLE_PRIMES))]
+    for _ in range(max(args.warmup, 0)):
+        reference_sample(primes[:1] if args.warmup > 1 else primes)
+    total_n, total_s, kind = 0, 0.0, "reference"
+    for _ in range(args.steps):
+        n, s, kind = reference_sample(primes)
+        total_n += n
+        total_s += s
+    value = total_n / total_s
+    sample = (f"per step: Genus::hecke_matrix_sparse(p) int64 on the same genus for the {len(primes)} primes "
+              f"{primes[0]}..{primes[-1]}, one OS process per prime on {cores} host cores "
+              f"(full-size p~10^4 costs ~50 s per prime per core)")
+    line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * total_s / max(args.steps, 1), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="int64", data="synthetic",
+                config=dict(workload=workload_name(PRIMES_DESC[0]), sample=sample),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=len(primes), kind=kind, sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precise", action="store_true", help="checked 128-bit mode instead of int64")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device; this path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from ternary_birch_b200 import Genus, cabi, load_genus_table, shard
+
+    table = load_genus_table(TABLE)
+    p = PRIMES_DESC[rank % len(PRIMES_DESC)]
+    N, K = table.N, table.K
+    neighbors_per_step = N * (p + 1)
+    stream = torch.cuda.current_stream()
+    g = Genus(table, precise=args.precise, stream=stream.cuda_stream)
+    L = cabi.lib()
+    launches0 = L.tb_launch_count()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident arm (`value`) -------------------------------------
+    def step_resident():
+        res = g.hecke_device(p)
+        return res
+
+    for _ in range(args.warmup):
+        step_resident().close()
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    if rank == 0:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    kernel_ms, rows_ms = [], []
+    launches_before = L.tb_launch_count()
+    last = None
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)                      # L2 flush between timed iterations (untimed)
+        starts[i].record(stream)
+        if last is not None:
+            last.close()
+        last = step_resident()
+        stops[i].record(stream)
+        a, b, _ = g.last_kernel_time()
+        kernel_ms.append(a)
+        rows_ms.append(b)
+    sync_all()
+    launches_timed = L.tb_launch_count() - launches_before
+    clocks = sampler.stop() if rank == 0 else None
+    my_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+    t = torch.tensor([my_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    total_neighbors = 0
+    for r in range(world):
+        total_neighbors += N * (PRIMES_DESC[r % len(PRIMES_DESC)] + 1) * args.steps
+    value = total_neighbors / (total_ms * 1e-3)
+
+    # ---- end-to-end arm (`e2e`): host buffers in, host CSR out, every step ----
+    C = 1 << K
+    shapes = [last.shape(k) for k in range(C)]
+    pinned = []
+    for rows, _, nnz in shapes:
+        pinned.append((torch.empty(max(nnz, 1) + 4096, dtype=torch.int32).pin_memory(),
+                       torch.empty(max(nnz, 1) + 4096, dtype=torch.int32).pin_memory(),
+                       torch.empty(rows + 1, dtype=torch.int32).pin_memory()))
+    h2d_bytes = g.table_bytes() + 12 * N
+    d2h_bytes = sum(4 * (2 * nnz + rows + 1) for rows, _, nnz in shapes)
+    last.close()
+
+    def step_e2e():
+        g.upload()                                   # genus table + per-prime inputs: host -> device
+        res = g.hecke_device(p)
+        for k in range(C):
+            d, i_, ptr = pinned[k]
+            rows, _, nnz = res.shape(k)
+            assert nnz <= d.numel()
+            res.copy_sparse_to(k, d.data_ptr(), i_.data_ptr(), ptr.data_ptr())
+        res.close()
+
+    step_e2e()
+    sync_all()
+    e_starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    e_stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        e_starts[i].record(stream)
+        step_e2e()
+        e_stops[i].record(stream)
+    sync_all()
+    wall_e2e = time.perf_counter() - wall0
+    e_ms = sum(s.elapsed_time(e) for s, e in zip(e_starts, e_stops))
+    t = torch.tensor([max(e_ms, wall_e2e * 1e3 if world == 1 else e_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total_neighbors / (float(t.item()) * 1e-3)
+
+    # ---- final integer gather of the Hecke rows (once, untimed region) -------
+    gather_ms = None
+    if world > 1:
+        local = g.hecke_matrix_sparse(p)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        got = shard.gather_csr(local, device=dev)
+        torch.cuda.synchronize()
+        gather_ms = (time.perf_counter() - t0) * 1e3
+        if rank == 0:
+            assert len(got) == world and all(len(x) == C for x in got)
+
+    # ---- roofline of the dominant kernel (neighbors_kernel) ------------------
+    peak = None
+    if rank == 0:
+        import ctypes
+        a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        cabi.check(L.tb_int_peak(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        peak = dict(imad=a.value, alu=b.value, mixed=c.value)
+    kms = sorted(kernel_ms)[len(kernel_ms) // 2]
+    rms = sorted(rows_ms)[len(rows_ms) // 2]
+
+    if rank == 0:
+        w32 = int32_ops_per_neighbor(p, K)
+        achieved = neighbors_per_step * w32 / (kms * 1e-3) / 1e12
+        measured_peak = max(peak["mixed"], peak["imad"], peak["alu"]) / 1e12
+        peaks_file = ROOT / "MEASURED_PEAKS.json"
+        hbm_peak = json.load(open(peaks_file))["hbm_gbs"] if peaks_file.exists() else 6650.0
+        # algorithmic DRAM-side bytes per neighbor: the 4-byte packed word written, plus the packed
+        # word re-read 3x by the row kernels; the genus table (<3 MB) stays in L2
+        hbm_achieved = neighbors_per_step * 4.0 / (kms * 1e-3) / 1e9
+        traffic = None
+        tf = ROOT / "profiles" / "neighbors_kernel_traffic.json"
+        if tf.exists():
+            traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+        roofline = dict(bound="int32-issue", achieved=achieved, peak=measured_peak, unit="Tint32op/s",
+                        frac=achieved / measured_peak, traffic=traffic,
+                        kernel="neighbors_kernel<W64,PACKED>", kernel_ms=kms, rows_kernels_ms=rms,
+                        int32_ops_per_neighbor=w32, peak_source="tb_int_peak microbenchmark, measured in this run "
+                        "(IMAD/IADD3+LOP3 chains on all SMs)", peak_detail=peak,
+                        hbm=dict(achieved=hbm_achieved, peak=hbm_peak, unit="GB/s", frac=hbm_achieved / hbm_peak,
+                                 peak_source="MEASURED_PEAKS.json" if peaks_file.exists() else "fallback"))
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            primes = REF_SAMPLE_PRIMES[:min(cores, len(REF_SAMPLE_PRIMES))]
+            n, s, kind = reference_sample(primes, precise=args.precise)
+            cpu = dict(value=n / s, unit=UNIT, cores=len(primes), kind=kind,
+                       sample=f"same genus, Genus::hecke_matrix_sparse(p) {'GMP' if args.precise else 'int64'} for the "
+                              f"{len(primes)} primes {primes[0]}..{primes[-1]}, one process per prime; {s:.1f} s wall")
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="int128-checked" if args.precise else "int64", data="synthetic",
+                    config=dict(workload=workload_name(p), neighbors_per_step_per_gpu=neighbors_per_step,
+                                l2="flushed between timed steps (256 MB write); the 412 MB packed-word stream "
+                                   "exceeds L2, the 3 MB genus table is L2-resident by design",
+                                sharding="one T_p per rank per step (prime axis), no data-path collective"),
+                    roofline=roofline, cpu_baseline=cpu,
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes),
+                    gpu_launches=int(launches_timed), clocks=clocks, T_p_wall_ms=total_ms / args.steps,
+                    final_gather_ms=gather_ms)
+        print(json.dumps(line), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -184,6 +184,31 @@ struct DevBuf {
     }
 };
 
+// Stream-ordered allocation from the device's default memory pool (kept warm:
+// the release threshold is raised in tb_genus_create), for per-call results.
+template <class T>
+struct PoolBuf {
+    T *ptr = nullptr;
+    size_t cap = 0;
+    cudaStream_t stream = 0;
+    cudaError_t reserve(size_t n, cudaStream_t st)
+    {
+        if (n <= cap) return cudaSuccess;
+        release();
+        stream = st;
+        size_t want = std::max(n, (size_t)16);
+        cudaError_t e = cudaMallocAsync((void **)&ptr, want * sizeof(T), st);
+        if (e == cudaSuccess) cap = want; else ptr = nullptr;
+        return e;
+    }
+    void release()
+    {
+        if (ptr) cudaFreeAsync(ptr, stream);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
 struct PrimeState {
     uint64_t p = 0;
     PrimeCtx pc;
@@ -208,7 +233,13 @@ struct tb_genus {
     DevBuf<RepPrime> d_rp;
     int rp_begin = -1, rp_rows = 0;
     DevBuf<u64> d_err;
+    DevBuf<int> d_tab;          // rowbase | rowfirst | rowcount   (row kernels)
+    DevBuf<i64> d_nnz;          // nnz | nnzbase
     u64 *h_err = nullptr;       // pinned [2]
+    i64 *h_nnz = nullptr;       // pinned [2 * 2^K]
+    int *h_tab = nullptr;       // pinned [3 * 2^K]
+    char *h_table = nullptr;    // pinned staging of the genus table upload
+    size_t h_table_bytes = 0;
     uint32_t *h_base = nullptr; // pinned staging
     size_t h_base_cap = 0;
 
@@ -224,7 +255,7 @@ struct tb_hecke {
     int rep_begin = 0, rep_end = 0;
     std::vector<int> rows, rowfirst, rowbase;
     std::vector<int64_t> nnz, nnzbase;
-    DevBuf<int> d_indptr, d_data, d_indices;
+    PoolBuf<int> d_indptr, d_data, d_indices;
 };
 
 struct tb_isoseq {
@@ -259,10 +290,31 @@ static int require_device()
 static int upload_table(tb_genus *g, const tb_genus_desc *d)
 {
     const int N = g->N, K = g->K;
-    std::vector<i64> cur((size_t)N * TB_REC_WORDS), rep((size_t)N * TB_REC_WORDS), disc(N);
+    int lg = 4;
+    while ((1ll << lg) < N) ++lg;
+    const u32 slots = 1u << (lg + 1);
+    // one pinned staging arena: cur | rep | disc | slots | lut
+    const size_t rec_bytes = (size_t)N * TB_REC_WORDS * sizeof(i64);
+    const size_t disc_bytes = (size_t)N * sizeof(i64);
+    const size_t slot_bytes = (size_t)slots * sizeof(int);
+    const size_t lut_bytes = ((size_t)N << K) * sizeof(int);
+    const size_t total = 2 * rec_bytes + disc_bytes + slot_bytes + lut_bytes;
+    if (total > g->h_table_bytes)
+    {
+        if (g->h_table) cudaFreeHost(g->h_table);
+        g->h_table = nullptr;
+        g->h_table_bytes = 0;
+        TB_CUDA(cudaMallocHost((void **)&g->h_table, total));
+        g->h_table_bytes = total;
+    }
+    i64 *cur = (i64 *)g->h_table;
+    i64 *rep = (i64 *)(g->h_table + rec_bytes);
+    i64 *disc = (i64 *)(g->h_table + 2 * rec_bytes);
+    int *table = (int *)(g->h_table + 2 * rec_bytes + disc_bytes);
+    int *lut = (int *)(g->h_table + 2 * rec_bytes + disc_bytes + slot_bytes);
     for (int n = 0; n < N; ++n)
     {
-        i64 *c = &cur[(size_t)n * TB_REC_WORDS], *r = &rep[(size_t)n * TB_REC_WORDS];
+        i64 *c = cur + (size_t)n * TB_REC_WORDS, *r = rep + (size_t)n * TB_REC_WORDS;
         for (int i = 0; i < 6; ++i) c[i] = r[i] = d->q[6 * n + i];
         c[6] = r[6] = d->scalar[n];
         for (int i = 0; i < 9; ++i) { c[7 + i] = d->s[9 * n + i]; r[7 + i] = d->sinv[9 * n + i]; }
@@ -271,11 +323,8 @@ static int upload_table(tb_genus *g, const tb_genus_desc *d)
         disc[n] = (i64)(a * (4ull * b * cc - f * f) - b * gg * gg + h * (f * gg - cc * h));
     }
     // open-addressing table of representatives: 2 * 2^ceil(log2 N) slots (>= 32), linear probing,
-    // keyed by the reference's FNV hash of the six coefficients.
-    int lg = 4;
-    while ((1ll << lg) < N) ++lg;
-    const u32 slots = 1u << (lg + 1);
-    std::vector<int> table(slots, -1);
+    // keyed by the reference's FNV hash of the six coefficients (HashMap.h:10-24, QuadForm.cpp:779-803).
+    for (u32 i = 0; i < slots; ++i) table[i] = -1;
     for (int n = 0; n < N; ++n)
     {
         u64 fnv = 0x811c9dc5ull;
@@ -284,16 +333,17 @@ static int upload_table(tb_genus *g, const tb_genus_desc *d)
         while (table[s] != -1) s = (s + 1) & (slots - 1);
         table[s] = n;
     }
-    TB_CUDA(g->d_cur.reserve(cur.size()));
-    TB_CUDA(g->d_rep.reserve(rep.size()));
+    memcpy(lut, d->lut, lut_bytes);
+    TB_CUDA(g->d_cur.reserve((size_t)N * TB_REC_WORDS));
+    TB_CUDA(g->d_rep.reserve((size_t)N * TB_REC_WORDS));
     TB_CUDA(g->d_disc.reserve(N));
     TB_CUDA(g->d_slots.reserve(slots));
     TB_CUDA(g->d_lut.reserve((size_t)N << K));
-    TB_CUDA(cudaMemcpyAsync(g->d_cur.ptr, cur.data(), cur.size() * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
-    TB_CUDA(cudaMemcpyAsync(g->d_rep.ptr, rep.data(), rep.size() * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
-    TB_CUDA(cudaMemcpyAsync(g->d_disc.ptr, disc.data(), N * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
-    TB_CUDA(cudaMemcpyAsync(g->d_slots.ptr, table.data(), slots * sizeof(int), cudaMemcpyHostToDevice, g->stream));
-    TB_CUDA(cudaMemcpyAsync(g->d_lut.ptr, d->lut, ((size_t)N << K) * sizeof(int), cudaMemcpyHostToDevice, g->stream));
+    TB_CUDA(cudaMemcpyAsync(g->d_cur.ptr, cur, rec_bytes, cudaMemcpyHostToDevice, g->stream));
+    TB_CUDA(cudaMemcpyAsync(g->d_rep.ptr, rep, rec_bytes, cudaMemcpyHostToDevice, g->stream));
+    TB_CUDA(cudaMemcpyAsync(g->d_disc.ptr, disc, disc_bytes, cudaMemcpyHostToDevice, g->stream));
+    TB_CUDA(cudaMemcpyAsync(g->d_slots.ptr, table, slot_bytes, cudaMemcpyHostToDevice, g->stream));
+    TB_CUDA(cudaMemcpyAsync(g->d_lut.ptr, lut, lut_bytes, cudaMemcpyHostToDevice, g->stream));
     TB_CUDA(cudaStreamSynchronize(g->stream));
 
     GenusCtx &gc = g->gc;
@@ -329,7 +379,19 @@ extern "C" int tb_genus_create(const tb_genus_desc *d, tb_genus **out)
     g->lut.assign(d->lut, d->lut + ((size_t)g->N << g->K));
     if (int rc = upload_table(g.get(), d)) return rc;
     TB_CUDA(g->d_err.reserve(2));
+    TB_CUDA(g->d_tab.reserve(3 * (size_t)C));
+    TB_CUDA(g->d_nnz.reserve(2 * (size_t)C));
     TB_CUDA(cudaMallocHost((void **)&g->h_err, 2 * sizeof(u64)));
+    TB_CUDA(cudaMallocHost((void **)&g->h_nnz, 2 * (size_t)C * sizeof(i64)));
+    TB_CUDA(cudaMallocHost((void **)&g->h_tab, 3 * (size_t)C * sizeof(int)));
+    {
+        int dev = 0;
+        cudaMemPool_t pool;
+        TB_CUDA(cudaGetDevice(&dev));
+        TB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long keep = ~0ull;
+        TB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     TB_CUDA(cudaEventCreate(&g->ev0));
     TB_CUDA(cudaEventCreate(&g->ev1));
     TB_CUDA(cudaEventCreate(&g->ev2));
@@ -354,7 +416,11 @@ extern "C" void tb_genus_destroy(tb_genus *g)
     if (!g) return;
     g->d_cur.release(); g->d_rep.release(); g->d_disc.release(); g->d_slots.release(); g->d_lut.release();
     g->d_invlut.release(); g->d_base.release(); g->d_W.release(); g->d_rp.release(); g->d_err.release();
+    g->d_tab.release(); g->d_nnz.release();
     if (g->h_err) cudaFreeHost(g->h_err);
+    if (g->h_nnz) cudaFreeHost(g->h_nnz);
+    if (g->h_tab) cudaFreeHost(g->h_tab);
+    if (g->h_table) cudaFreeHost(g->h_table);
     if (g->h_base) cudaFreeHost(g->h_base);
     if (g->ev0) cudaEventDestroy(g->ev0);
     if (g->ev1) cudaEventDestroy(g->ev1);
@@ -539,7 +605,7 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
         h->rowbase[k] = total_ptr;
         total_ptr += cnt + 1;
     }
-    TB_CUDA(h->d_indptr.reserve(total_ptr));
+    TB_CUDA(h->d_indptr.reserve(total_ptr, g->stream));
     TB_CUDA(cudaMemsetAsync(h->d_indptr.ptr, 0, (size_t)total_ptr * sizeof(int), g->stream));
     if (rows == 0)
     {
@@ -552,16 +618,14 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     TB_CUDA(g->d_W.reserve((size_t)rows * P1));
 
     // small device-side tables for the row kernels
-    DevBuf<int> d_tab;      // rowbase | rowfirst | rowcount
-    DevBuf<i64> d_nnz;      // nnz | nnzbase
-    TB_CUDA(d_tab.reserve(3 * (size_t)C));
-    TB_CUDA(d_nnz.reserve(2 * (size_t)C));
-    std::vector<int> tab(3 * (size_t)C);
+    DevBuf<int> &d_tab = g->d_tab;
+    DevBuf<i64> &d_nnz = g->d_nnz;
+    int *tab = g->h_tab;
     for (int k = 0; k < C; ++k) { tab[k] = h->rowbase[k]; tab[C + k] = h->rowfirst[k]; tab[2 * C + k] = h->rows[k]; }
-    TB_CUDA(cudaMemcpyAsync(d_tab.ptr, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, g->stream));
+    TB_CUDA(cudaMemcpyAsync(d_tab.ptr, tab, 3 * (size_t)C * sizeof(int), cudaMemcpyHostToDevice, g->stream));
 
     TB_CUDA(cudaEventRecord(g->ev0, g->stream));
-    if (int rc = launch_neighbors<MODE_PACKED>(g, precise, rb, rows, g->d_W.ptr, nullptr)) { d_tab.release(); d_nnz.release(); return rc; }
+    if (int rc = launch_neighbors<MODE_PACKED>(g, precise, rb, rows, g->d_W.ptr, nullptr)) { return rc; }
     TB_CUDA(cudaEventRecord(g->ev1, g->stream));
 
     RowLaunch R;
@@ -574,7 +638,6 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     const size_t smem = rows_smem_bytes(N, P1);
     if (smem > 227 * 1024)
     {
-        d_tab.release(); d_nnz.release();
         return fail(TB_ERR_RUNTIME, "libtbirch: row accumulation needs more shared memory than one SM has for this (N, p)");
     }
     int threads = (int)std::min<u32>(512, std::max<u32>(64, (P1 + 31) / 32 * 32));
@@ -588,15 +651,17 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     TB_CUDA(cudaGetLastError());
 
     TB_CUDA(cudaMemcpyAsync(g->h_err, g->d_err.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, g->stream));
-    TB_CUDA(cudaMemcpyAsync(h->nnz.data(), d_nnz.ptr, C * sizeof(i64), cudaMemcpyDeviceToHost, g->stream));
+    TB_CUDA(cudaMemcpyAsync(g->h_nnz, d_nnz.ptr, C * sizeof(i64), cudaMemcpyDeviceToHost, g->stream));
     TB_CUDA(cudaStreamSynchronize(g->stream));
-    if (int rc = check_errors(g)) { d_tab.release(); d_nnz.release(); return rc; }
+    if (int rc = check_errors(g)) { return rc; }
+    for (int k = 0; k < C; ++k) h->nnz[k] = g->h_nnz[k];
 
     int64_t total_nnz = 0;
     for (int k = 0; k < C; ++k) { h->nnzbase[k] = total_nnz; total_nnz += h->nnz[k]; }
-    TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(total_nnz, 1)));
-    TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(total_nnz, 1)));
-    TB_CUDA(cudaMemcpyAsync(d_nnz.ptr + C, h->nnzbase.data(), C * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
+    TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(total_nnz, 1), g->stream));
+    TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(total_nnz, 1), g->stream));
+    for (int k = 0; k < C; ++k) g->h_nnz[C + k] = h->nnzbase[k];
+    TB_CUDA(cudaMemcpyAsync(d_nnz.ptr + C, g->h_nnz + C, C * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
     R.data = h->d_data.ptr; R.indices = h->d_indices.ptr;
     rows_kernel<true><<<rows, threads, smem, g->stream>>>(R);
     ++g_launches;
@@ -607,7 +672,6 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     cudaEventElapsedTime(&g->last_ms_rows, g->ev1, g->ev2);
     g->last_neighbors = (int64_t)rows * P1;
     g->timing_valid = true;
-    d_tab.release(); d_nnz.release();
     *out = h.release();
     return TB_OK;
 }
