@@ -411,6 +411,8 @@ __global__ void eigen_dot_kernel(const u32 *W, u32 P1, int K, int N, const int *
 template <int KIND>
 __global__ void __launch_bounds__(256) int_peak_kernel(u32 *sink, int iters, u32 seed)
 {
+    // KIND 0: IMAD only (fma pipe); KIND 1: LOP3 only (alu pipe);
+    // KIND 2: one IMAD + one IADD3 per chain step (both pipes, issue-limited)
     u32 x0 = seed + threadIdx.x, x1 = x0 * 3u + 1u, x2 = x0 * 5u + 2u, x3 = x0 * 7u + 3u;
     u32 x4 = x0 * 11u + 4u, x5 = x0 * 13u + 5u, x6 = x0 * 17u + 6u, x7 = x0 * 19u + 7u;
     const u32 m = seed | 1u, c = seed ^ 0x9e3779b9u;
@@ -424,10 +426,15 @@ __global__ void __launch_bounds__(256) int_peak_kernel(u32 *sink, int iters, u32
                 x0 = x0 * m + c; x1 = x1 * m + c; x2 = x2 * m + c; x3 = x3 * m + c;
                 x4 = x4 * m + c; x5 = x5 * m + c; x6 = x6 * m + c; x7 = x7 * m + c;
             }
-            if (KIND == 1 || KIND == 2)
+            if (KIND == 1)
             {
-                x0 = (x0 ^ c) + (x1 & m); x1 = (x1 ^ c) + (x2 & m); x2 = (x2 ^ c) + (x3 & m); x3 = (x3 ^ c) + (x4 & m);
-                x4 = (x4 ^ c) + (x5 & m); x5 = (x5 ^ c) + (x6 & m); x6 = (x6 ^ c) + (x7 & m); x7 = (x7 ^ c) + (x0 & m);
+                x0 ^= x1 & m; x1 ^= x2 & c; x2 ^= x3 & m; x3 ^= x4 & c;
+                x4 ^= x5 & m; x5 ^= x6 & c; x6 ^= x7 & m; x7 ^= x0 & c;
+            }
+            if (KIND == 2)
+            {
+                x0 += x1 + m; x1 += x2 + m; x2 += x3 + m; x3 += x4 + m;
+                x4 += x5 + m; x5 += x6 + m; x6 += x7 + m; x7 += x0 + m;
             }
         }
     }

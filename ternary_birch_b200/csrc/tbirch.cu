@@ -955,10 +955,11 @@ extern "C" int tb_int_peak(double *imad, double *iadd, double *mixed)
 {
     if (int rc = require_device()) return rc;
     double a = 0, b = 0, c = 0;
-    // per inner iteration: 16 unrolled steps x 8 chains; KIND 0: 1 IMAD each; KIND 1: 2 logic/add ops each; KIND 2: both
+    // per inner iteration: 16 unrolled steps x 8 chains; KIND 0: 1 IMAD each; KIND 1: 1 LOP3 each;
+    // KIND 2: 1 IMAD + 1 LOP3 each
     if (int rc = peak_one<0>(16.0 * 8.0, &a)) return rc;
-    if (int rc = peak_one<1>(16.0 * 8.0 * 2.0, &b)) return rc;
-    if (int rc = peak_one<2>(16.0 * 8.0 * 3.0, &c)) return rc;
+    if (int rc = peak_one<1>(16.0 * 8.0, &b)) return rc;
+    if (int rc = peak_one<2>(16.0 * 8.0 * 2.0, &c)) return rc;
     if (imad) *imad = a;
     if (iadd) *iadd = b;
     if (mixed) *mixed = c;
