@@ -94,8 +94,11 @@ neighbors_kernel(const __grid_constant__ GenusCtx gc, const __grid_constant__ Pr
     if (threadIdx.x == 0) *cta_flag_ptr() = 0u;
     __syncthreads();
 
-    const u64 i = (u64)blockIdx.x * TB_NBR_THREADS + threadIdx.x;
-    if (i < L.total)
+    // lanes past the end recompute the last neighbor (no early exit: the W64 reduce votes
+    // warp-wide) and skip the writes
+    const u64 i_raw = (u64)blockIdx.x * TB_NBR_THREADS + threadIdx.x;
+    const bool live = i_raw < L.total;
+    const u64 i = live ? i_raw : L.total - 1;
     {
         u64 t64;
         const u64 row = udivmod(i, L.dP1, t64);
@@ -105,10 +108,13 @@ neighbors_kernel(const __grid_constant__ GenusCtx gc, const __grid_constant__ Pr
 
         Neighbor<Z> o;
         const int status = one_neighbor<Z>(n, t, rp, pc, gc, MODE == MODE_ISOSEQ, o);
-        if (status == NBR_OVERFLOW) atomicMin(L.err + 0, i);
-        else if (status == NBR_NOT_FOUND) atomicMin(L.err + 1, i);
+        if (status == NBR_OVERFLOW && live) atomicMin(L.err + 0, i);
+        else if (status == NBR_NOT_FOUND && live) atomicMin(L.err + 1, i);
 
-        if (MODE == MODE_PACKED)
+        if (!live)
+        {
+        }
+        else if (MODE == MODE_PACKED)
         {
             L.W[i] = status == NBR_OK ? (((u32)o.r << gc.K) | o.spin) : 0xffffffffu;
         }

@@ -528,6 +528,241 @@ __device__ __forceinline__ bool eisenstein_reduce(Form<Z> &q, Iso<Z> &s)
 }
 
 // ---------------------------------------------------------------------------
+// W64 fast path of the same reduction: identical arithmetic and operation order,
+// restructured for SIMT.
+//   * The loop body is branch-free: every lane runs the same instruction stream
+//     (shears with t = 0 are no-ops, swaps and sign flips are selects), so a warp
+//     diverges only on the trip count.  Lanes that have met the exit test are
+//     frozen by masking their quotients and predicates.
+//   * Quotients use one FP64 reciprocal (MUFU.RCP64H + two Newton steps) and an
+//     exact integer correction instead of a division routine; inputs outside the
+//     proven-exact range take the literal reference ladder under a warp vote.
+//   * Column negations of the isometry are tracked as three lazy sign bits and
+//     folded into the shear multipliers; columns are negated once, after the loop.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double rcp_f64(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// floor(n / d) given rd ~ 1/d; exact when 0 <= n < 2^62, 0 < d and n/d < 2^49
+// (|fl(n) rd - n/d| < 1/2 there, so one correction step each way suffices).
+__device__ __forceinline__ i64 floor_div_rcp(i64 n, i64 d, double rd)
+{
+    i64 q = __double2ll_rz(__ll2double_rn(n) * rd);
+    i64 r = (i64)((u64)n - (u64)q * (u64)d);
+    if (r < 0) { q -= 1; r += d; }
+    if (r >= d) { q += 1; }
+    return q;
+}
+
+__device__ __forceinline__ bool quotient_in_range(i64 n, i64 d)
+{
+    return n >= 0 && d > 0 && n < (1ll << 62) && (n >> 49) < d;
+}
+
+// cold path: the literal reference ladder (wrapped / out-of-range operands only)
+__device__ __noinline__ i64 quotient_cold(i64 n, i64 d) { return ref_quotient(W64(n), W64(d)).v; }
+
+// the reference's shear multiplier  t = a >= h ? (a-h) div 2a : -((a+h-1) div 2a)   (551-558)
+__device__ __forceinline__ i64 shear_t(i64 a, i64 h, i64 den, double rden)
+{
+    const bool ge = a >= h;
+    const i64 num = ge ? (i64)((u64)a - (u64)h) : (i64)((u64)a + (u64)h - 1ull);
+    i64 q;
+    if (__all_sync(0xffffffffu, quotient_in_range(num, den)))
+        q = floor_div_rcp(num, den, rden);
+    else
+        q = quotient_cold(num, den);
+    return ge ? q : (i64)(0ull - (u64)q);
+}
+
+__device__ __forceinline__ i64 cneg64(i64 x, bool neg)
+{
+    const u64 m = neg ? ~0ull : 0ull;
+    return (i64)(((u64)x ^ m) - m);
+}
+__device__ __forceinline__ void cswap64(bool p, i64 &x, i64 &y)
+{
+    const i64 t = p ? y : x;
+    y = p ? x : y;
+    x = t;
+}
+__device__ __forceinline__ void cswap_w(bool p, W64 &x, W64 &y) { cswap64(p, x.v, y.v); }
+__device__ __forceinline__ u64 uabs64(i64 x) { return x < 0 ? 0ull - (u64)x : (u64)x; }
+// the reference compares std::abs values as signed int64 (abs(INT64_MIN) stays negative)
+__device__ __forceinline__ bool abs_gt(i64 x, i64 y) { return (i64)uabs64(x) > (i64)uabs64(y); }
+__device__ __forceinline__ bool abs_le(i64 x, i64 y) { return (i64)uabs64(x) <= y; }
+
+__device__ __forceinline__ bool eisenstein_reduce(Form<W64> &q, Iso<W64> &s)
+{
+    i64 a = q.a.v, b = q.b.v, c = q.c.v, f = q.f.v, g = q.g.v, h = q.h.v;
+    // lazy column signs: actual column i = (sg_i ? -1 : +1) * stored column i
+    bool sg1 = false, sg2 = false, sg3 = false;
+    bool active = true;
+    int iters = 0;
+    // every lane of the warp gets here (one_neighbor keeps failed / out-of-range lanes in
+    // step on a dummy form), so the votes below use the full mask
+    const unsigned warp = 0xffffffffu;
+    __syncwarp(warp);
+
+    while (__any_sync(warp, active))
+    {
+        if (++iters > TB_REDUCE_CAP) return false;
+
+        // -- a + b + f + g + h < 0                                 542-549
+        {
+            const i64 t = (i64)((u64)a + (u64)b + (u64)f + (u64)g + (u64)h);
+            const bool fix = active && t < 0;
+            if (__any_sync(warp, fix))
+            {
+                // c3 += c1 + c2 on actual columns: C3 += (sg1^sg3 ? -C1 : C1) + (sg2^sg3 ? -C2 : C2)
+                const bool n1 = sg1 != sg3, n2 = sg2 != sg3;
+                if (fix)
+                {
+                    s.a13.v = (i64)((u64)s.a13.v + (u64)cneg64(s.a11.v, n1) + (u64)cneg64(s.a12.v, n2));
+                    s.a23.v = (i64)((u64)s.a23.v + (u64)cneg64(s.a21.v, n1) + (u64)cneg64(s.a22.v, n2));
+                    s.a33.v = (i64)((u64)s.a33.v + (u64)cneg64(s.a31.v, n1) + (u64)cneg64(s.a32.v, n2));
+                    c = (i64)((u64)c + (u64)t);
+                    f = (i64)((u64)f + (u64)h + 2ull * (u64)b);
+                    g = (i64)((u64)g + (u64)h + 2ull * (u64)a);
+                }
+            }
+        }
+
+        // -- shear 1: col2 += t col1                               551-567
+        i64 den = (i64)((u64)a << 1);
+        double rden = rcp_f64(__ll2double_rn(den));
+        {
+            i64 t = shear_t(a, h, den, rden);
+            t = active ? t : 0;
+            const u64 ts = (u64)cneg64(t, sg1 != sg2);
+            s.a12.v = (i64)((u64)s.a12.v + ts * (u64)s.a11.v);
+            s.a22.v = (i64)((u64)s.a22.v + ts * (u64)s.a21.v);
+            s.a32.v = (i64)((u64)s.a32.v + ts * (u64)s.a31.v);
+            const u64 temp = (u64)a * (u64)t;
+            h = (i64)((u64)h + temp);
+            b = (i64)((u64)b + (u64)h * (u64)t);
+            f = (i64)((u64)f + (u64)g * (u64)t);
+            h = (i64)((u64)h + temp);
+        }
+        // -- shear 2: col3 += t col2                               569-585
+        {
+            const i64 den2 = (i64)((u64)b << 1);
+            const double rden2 = rcp_f64(__ll2double_rn(den2));
+            i64 t = shear_t(b, f, den2, rden2);
+            t = active ? t : 0;
+            const u64 ts = (u64)cneg64(t, sg2 != sg3);
+            s.a13.v = (i64)((u64)s.a13.v + ts * (u64)s.a12.v);
+            s.a23.v = (i64)((u64)s.a23.v + ts * (u64)s.a22.v);
+            s.a33.v = (i64)((u64)s.a33.v + ts * (u64)s.a32.v);
+            const u64 temp = (u64)b * (u64)t;
+            f = (i64)((u64)f + temp);
+            c = (i64)((u64)c + (u64)f * (u64)t);
+            g = (i64)((u64)g + (u64)h * (u64)t);
+            f = (i64)((u64)f + temp);
+        }
+        // -- shear 3: col3 += t col1   (a, and so 2a, unchanged)    587-603
+        {
+            i64 t = shear_t(a, g, den, rden);
+            t = active ? t : 0;
+            const u64 ts = (u64)cneg64(t, sg1 != sg3);
+            s.a13.v = (i64)((u64)s.a13.v + ts * (u64)s.a11.v);
+            s.a23.v = (i64)((u64)s.a23.v + ts * (u64)s.a21.v);
+            s.a33.v = (i64)((u64)s.a33.v + ts * (u64)s.a31.v);
+            const u64 temp = (u64)a * (u64)t;
+            g = (i64)((u64)g + temp);
+            c = (i64)((u64)c + (u64)g * (u64)t);
+            f = (i64)((u64)f + (u64)h * (u64)t);
+            g = (i64)((u64)g + temp);
+        }
+
+        // -- sort a <= b <= c with the reference's tie-breaks      605-624
+        {
+            const bool p = active && (a > b || (a == b && abs_gt(f, g)));
+            cswap64(p, a, b); cswap64(p, f, g);
+            cswap_w(p, s.a11, s.a12); cswap_w(p, s.a21, s.a22); cswap_w(p, s.a31, s.a32);
+            // (c1, c2, c3) <- (-c2, -c1, -c3)
+            const bool o1 = sg1, o2 = sg2;
+            sg1 = p ? !o2 : o1; sg2 = p ? !o1 : o2; sg3 = p ? !sg3 : sg3;
+        }
+        {
+            const bool p = active && (b > c || (b == c && abs_gt(g, h)));
+            cswap64(p, b, c); cswap64(p, g, h);
+            cswap_w(p, s.a12, s.a13); cswap_w(p, s.a22, s.a23); cswap_w(p, s.a32, s.a33);
+            // (c1, c2, c3) <- (-c1, -c3, -c2)
+            const bool o2 = sg2, o3 = sg3;
+            sg2 = p ? !o3 : o2; sg3 = p ? !o2 : o3; sg1 = p ? !sg1 : sg1;
+        }
+        {
+            const bool p = active && (a > b || (a == b && abs_gt(f, g)));
+            cswap64(p, a, b); cswap64(p, f, g);
+            cswap_w(p, s.a11, s.a12); cswap_w(p, s.a21, s.a22); cswap_w(p, s.a31, s.a32);
+            const bool o1 = sg1, o2 = sg2;
+            sg1 = p ? !o2 : o1; sg2 = p ? !o1 : o2; sg3 = p ? !sg3 : sg3;
+        }
+
+        // -- sign normalisation                                      626-687
+        {
+            const bool fneg = f < 0, gneg = g < 0, hneg = h < 0;
+            const bool fz = f == 0, gz = g == 0, hz = h == 0;
+            const bool even_neg = ((int)fneg + (int)gneg + (int)hneg) % 2 == 0;
+            const bool fgh = !fz && !gz && !hz && even_neg;
+            bool s1 = !fneg && !fz, s2 = !gneg && !gz, s3 = !hneg && !hz;
+            const bool odd = ((int)s1 + (int)s2 + (int)s3) % 2 == 1;
+            s1 = s1 || (odd && fz);
+            s2 = s2 || (odd && !fz && gz);
+            s3 = s3 || (odd && !fz && !gz && hz);
+            const bool n1 = active && (fgh ? fneg : s1);
+            const bool n2 = active && (fgh ? gneg : s2);
+            const bool n3 = active && (fgh ? hneg : s3);
+            f = cneg64(f, n1); g = cneg64(g, n2); h = cneg64(h, n3);
+            sg1 = sg1 != n1; sg2 = sg2 != n2; sg3 = sg3 != n3;
+        }
+
+        // -- exit test                                               689-690
+        const i64 sum = (i64)((u64)a + (u64)b + (u64)f + (u64)g + (u64)h);
+        const bool done = abs_le(f, b) && abs_le(g, a) && abs_le(h, a) && sum >= 0;
+        active = active && !done;
+    }
+
+    // materialise the lazy signs
+    s.a11.v = cneg64(s.a11.v, sg1); s.a21.v = cneg64(s.a21.v, sg1); s.a31.v = cneg64(s.a31.v, sg1);
+    s.a12.v = cneg64(s.a12.v, sg2); s.a22.v = cneg64(s.a22.v, sg2); s.a32.v = cneg64(s.a32.v, sg2);
+    s.a13.v = cneg64(s.a13.v, sg3); s.a23.v = cneg64(s.a23.v, sg3); s.a33.v = cneg64(s.a33.v, sg3);
+
+    // boundary fix-ups, rare: the branchy generic code                693-764
+    W64 A(a), B(b), C(c), F(f), G(g), H(h), t;
+    const W64 zero(0);
+    W64 sum = A + B + F + G + H;
+    if (sum.is_zero() && A.twice() + G.twice() + H > zero)
+    {
+        s.fix_sum();
+        C += sum;
+        F += H + B.twice(); F = -F;
+        G += H + A.twice(); G = -G;
+    }
+    if (A == -H && !G.is_zero()) { s.fix_ah(); F += G; F = -F; G = -G; H = -H; }
+    if (A == -G && !H.is_zero()) { s.fix_ag(); F += H; F = -F; H = -H; G += A.twice(); }
+    if (B == -F && !H.is_zero()) { s.fix_bf(); G += H; G = -G; H = -H; F += B.twice(); }
+    if (A == H && G > F.twice()) { s.edge_ah(); F = G - F; }
+    if (A == G && H > F.twice()) { s.edge_ag(); F = H - F; }
+    if (B == F && H > G.twice()) { s.edge_bf(); G = H - G; }
+    if (A == B && F.abs() > G.abs()) { s.swap12_neg(); t = A; A = B; B = t; t = G; G = F; F = t; }
+    if (B == C && G.abs() > H.abs()) { s.swap23_neg(); t = G; G = H; H = t; }
+    if (A == B && F.abs() > G.abs()) { s.swap12_neg(); t = G; G = F; F = t; }
+
+    q.a = A; q.b = B; q.c = C; q.f = F; q.g = G; q.h = H;
+    return true;
+}
+
+// ---------------------------------------------------------------------------
 // Genus lookup.  QuadForm::hash_value (QuadForm.cpp:779-803) + HashMap::indexof
 // (HashMap.h:68-89).  Returns the representative index or -1 ("Key not found.").
 // ---------------------------------------------------------------------------
@@ -655,8 +890,19 @@ __device__ __forceinline__ int one_neighbor(int n, u32 t, const RepPrime &rp, co
     const i64 *cur = gc.cur + (size_t)n * TB_REC_WORDS;
     Form<Z> q = load_form<Z>(cur);
     line_for_t(rp, t, pc, o.vx, o.vy, o.vz);
-    if (!build_neighbor(q, o.vx, o.vy, o.vz, __ldg(gc.disc + n), pc, o.q, o.s)) return NBR_OVERFLOW;
-    if (!eisenstein_reduce(o.q, o.s)) return NBR_OVERFLOW;
+    const bool built = build_neighbor(q, o.vx, o.vy, o.vz, __ldg(gc.disc + n), pc, o.q, o.s);
+    if (!built)
+    {
+        // keep the lane in step with its warp (the W64 reduce votes warp-wide): reduce the
+        // representative's own, already reduced, form; the result is discarded
+        const Z zero = Z(0), one = Z(1);
+        o.q = q;
+        o.s.a11 = one; o.s.a12 = zero; o.s.a13 = zero;
+        o.s.a21 = zero; o.s.a22 = one; o.s.a23 = zero;
+        o.s.a31 = zero; o.s.a32 = zero; o.s.a33 = one;
+    }
+    const bool reduced = eisenstein_reduce(o.q, o.s);
+    if (!built || !reduced) return NBR_OVERFLOW;
 
     const int r = genus_lookup(o.q, gc);                     // Genus.h:575
     if (r < 0) return NBR_NOT_FOUND;
