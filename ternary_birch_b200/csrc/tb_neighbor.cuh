@@ -35,6 +35,8 @@ struct RepPrime {
 struct PrimeCtx {
     u32 p;
     u32 use_lut;
+    u32 fp64_reduce;  // host-verified: isometry entries stay below 2^52 in the FP64 reduce loop
+    u32 pad;
     u64 pp;
     InvDiv dp;        // division by p
     InvDiv dpp;       // division by p^2
@@ -528,17 +530,34 @@ __device__ __forceinline__ bool eisenstein_reduce(Form<Z> &q, Iso<Z> &s)
 }
 
 // ---------------------------------------------------------------------------
-// W64 fast path of the same reduction: identical arithmetic and operation order,
-// restructured for SIMT.
-//   * The loop body is branch-free: every lane runs the same instruction stream
-//     (shears with t = 0 are no-ops, swaps and sign flips are selects), so a warp
-//     diverges only on the trip count.  Lanes that have met the exit test are
-//     frozen by masking their quotients and predicates.
-//   * Quotients use one FP64 reciprocal (MUFU.RCP64H + two Newton steps) and an
-//     exact integer correction instead of a division routine; inputs outside the
-//     proven-exact range take the literal reference ladder under a warp vote.
-//   * Column negations of the isometry are tracked as three lazy sign bits and
-//     folded into the shear multipliers; columns are negated once, after the loop.
+// FP64 fast path of the same reduction (both integer modes).
+//
+// B200's FP64 pipe issues DFMA/DADD/DSETP at the same rate as each integer pipe
+// and is otherwise idle in this kernel, while 64-bit integer compares, selects
+// and negations saturate the ALU pipe.  Every quantity in the reduction loop is
+// an integer, so it is computed EXACTLY in binary64 as long as it stays below
+// 2^53: a multiply-add is one DFMA (the product is never rounded separately), a
+// compare one DSETP (|x| is a free operand modifier), a sign flip one LOP3.
+//
+// Why the values stay small (positive definite form, exact arithmetic):
+//   * diagonal coefficients are values Q(v) of the current basis vectors; each
+//     shear replaces one by a not-larger value, swaps permute them and the
+//     "sum < 0" step replaces c by Q(1,1,1) < c: they never grow;
+//   * off-diagonals obey f^2 < 4bc, g^2 < 4ac, h^2 < 4ab, so |f|,|g|,|h| < 2 max(a,b,c);
+//   * a shear's intermediates are a t (|t| <= (|h|+a)/2a + 1), h + a t, and DFMA
+//     results that are themselves new coefficients: all below 5 max(a,b,c);
+//   * isometry columns are lattice vectors v with Q_rep(v) = p^2 * (diagonal
+//     coefficient), so |v_i| <= p sqrt(max(a,b,c) / lambda_min(Q_rep)); the host
+//     enables this path only when that bound is below 2^52 (PrimeCtx::fp64_reduce).
+// The loop is entered only when every lane's 15 inputs are below 2^50 in
+// magnitude (warp vote); otherwise the warp takes the integer loop above.
+//
+// SIMT shape: the body is branch-free (shears with t = 0 are no-ops, swaps and
+// sign flips are selects), so a warp diverges only on the trip count; finished
+// lanes are frozen by masking their quotients and predicates.  Column negations
+// of the isometry are three lazy sign bits folded into the shear multipliers.
+// The operation order is the reference's (QuadForm.h:540-691), so the isometry
+// is bit-identical.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double rcp_f64(double d)
 {
@@ -550,216 +569,225 @@ __device__ __forceinline__ double rcp_f64(double d)
     r = fma(r, e, r);
     return r;
 }
-
-// floor(n / d) given rd ~ 1/d; exact when 0 <= n < 2^62, 0 < d and n/d < 2^49
-// (|fl(n) rd - n/d| < 1/2 there, so one correction step each way suffices).
-__device__ __forceinline__ i64 floor_div_rcp(i64 n, i64 d, double rd)
+__device__ __forceinline__ double dflip(double x, bool neg)
 {
-    i64 q = __double2ll_rz(__ll2double_rn(n) * rd);
-    i64 r = (i64)((u64)n - (u64)q * (u64)d);
-    if (r < 0) { q -= 1; r += d; }
-    if (r >= d) { q += 1; }
-    return q;
+    return __hiloint2double(__double2hiint(x) ^ (neg ? (int)0x80000000 : 0), __double2loint(x));
 }
-
-__device__ __forceinline__ bool quotient_in_range(i64 n, i64 d)
+__device__ __forceinline__ void dswap(bool p, double &x, double &y)
 {
-    return n >= 0 && d > 0 && n < (1ll << 62) && (n >> 49) < d;
-}
-
-// cold path: the literal reference ladder (wrapped / out-of-range operands only)
-__device__ __noinline__ i64 quotient_cold(i64 n, i64 d) { return ref_quotient(W64(n), W64(d)).v; }
-
-// the reference's shear multiplier  t = a >= h ? (a-h) div 2a : -((a+h-1) div 2a)   (551-558)
-__device__ __forceinline__ i64 shear_t(i64 a, i64 h, i64 den, double rden)
-{
-    const bool ge = a >= h;
-    const i64 num = ge ? (i64)((u64)a - (u64)h) : (i64)((u64)a + (u64)h - 1ull);
-    i64 q;
-    if (__all_sync(0xffffffffu, quotient_in_range(num, den)))
-        q = floor_div_rcp(num, den, rden);
-    else
-        q = quotient_cold(num, den);
-    return ge ? q : (i64)(0ull - (u64)q);
-}
-
-__device__ __forceinline__ i64 cneg64(i64 x, bool neg)
-{
-    const u64 m = neg ? ~0ull : 0ull;
-    return (i64)(((u64)x ^ m) - m);
-}
-__device__ __forceinline__ void cswap64(bool p, i64 &x, i64 &y)
-{
-    const i64 t = p ? y : x;
+    const double t = p ? y : x;
     y = p ? x : y;
     x = t;
 }
-__device__ __forceinline__ void cswap_w(bool p, W64 &x, W64 &y) { cswap64(p, x.v, y.v); }
-__device__ __forceinline__ u64 uabs64(i64 x) { return x < 0 ? 0ull - (u64)x : (u64)x; }
-// the reference compares std::abs values as signed int64 (abs(INT64_MIN) stays negative)
-__device__ __forceinline__ bool abs_gt(i64 x, i64 y) { return (i64)uabs64(x) > (i64)uabs64(y); }
-__device__ __forceinline__ bool abs_le(i64 x, i64 y) { return (i64)uabs64(x) <= y; }
-
-__device__ __forceinline__ bool eisenstein_reduce(Form<W64> &q, Iso<W64> &s)
+// shear multiplier  t = a >= h ? floor((a-h)/2a) : -floor((a+h-1)/2a)   (QuadForm.h:551-558);
+// num >= 0, den > 0, num/den < 2^50: the rounded estimate is off by at most one.
+__device__ __forceinline__ double dshear_t(double a, double h, double den, double rden)
 {
-    i64 a = q.a.v, b = q.b.v, c = q.c.v, f = q.f.v, g = q.g.v, h = q.h.v;
-    // lazy column signs: actual column i = (sg_i ? -1 : +1) * stored column i
-    bool sg1 = false, sg2 = false, sg3 = false;
+    const bool ge = a >= h;
+    const double num = ge ? __dadd_rn(a, -h) : __dadd_rn(__dadd_rn(a, h), -1.0);
+    const double magic = 4503599627370496.0;   // 2^52
+    double q = __dadd_rn(__dadd_rn(__dmul_rn(num, rden), magic), -magic);
+    double r = fma(-q, den, num);               // exact
+    const bool lo = r < 0.0;
+    q = lo ? q - 1.0 : q;
+    r = lo ? r + den : r;
+    q = r >= den ? q + 1.0 : q;
+    return ge ? q : -q;
+}
+
+// 2^50 magnitude test on an int64
+__device__ __forceinline__ bool small50(i64 v) { return (u64)(v + (1ll << 50)) < (1ull << 51); }
+__device__ __forceinline__ bool fits50(W64 x) { return small50(x.v); }
+__device__ __forceinline__ bool fits50(C128 x) { return x.fits_i64() && small50((i64)x.lo); }
+
+struct DReduce {
+    double a, b, c, f, g, h;
+    double s11, s12, s13, s21, s22, s23, s31, s32, s33;
+};
+
+// Returns the trip count; the caller converts the state back and runs the
+// (rare, branchy) boundary fix-ups in integer arithmetic.
+__device__ __forceinline__ int reduce_loop_fp64(DReduce &d)
+{
+    double a = d.a, b = d.b, c = d.c, f = d.f, g = d.g, h = d.h;
+    double s11 = d.s11, s12 = d.s12, s13 = d.s13, s21 = d.s21, s22 = d.s22, s23 = d.s23;
+    double s31 = d.s31, s32 = d.s32, s33 = d.s33;
+    bool sg1 = false, sg2 = false, sg3 = false;   // actual column i = (sg_i ? -1 : 1) * stored column i
     bool active = true;
     int iters = 0;
-    // every lane of the warp gets here (one_neighbor keeps failed / out-of-range lanes in
-    // step on a dummy form), so the votes below use the full mask
     const unsigned warp = 0xffffffffu;
-    __syncwarp(warp);
+    double sum = (((a + b) + f) + g) + h;
 
     while (__any_sync(warp, active))
     {
-        if (++iters > TB_REDUCE_CAP) return false;
+        if (++iters > TB_REDUCE_CAP) break;
 
-        // -- a + b + f + g + h < 0                                 542-549
+        // a + b + f + g + h < 0                                      542-549
         {
-            const i64 t = (i64)((u64)a + (u64)b + (u64)f + (u64)g + (u64)h);
-            const bool fix = active && t < 0;
+            const bool fix = active && sum < 0.0;
             if (__any_sync(warp, fix))
             {
-                // c3 += c1 + c2 on actual columns: C3 += (sg1^sg3 ? -C1 : C1) + (sg2^sg3 ? -C2 : C2)
-                const bool n1 = sg1 != sg3, n2 = sg2 != sg3;
                 if (fix)
                 {
-                    s.a13.v = (i64)((u64)s.a13.v + (u64)cneg64(s.a11.v, n1) + (u64)cneg64(s.a12.v, n2));
-                    s.a23.v = (i64)((u64)s.a23.v + (u64)cneg64(s.a21.v, n1) + (u64)cneg64(s.a22.v, n2));
-                    s.a33.v = (i64)((u64)s.a33.v + (u64)cneg64(s.a31.v, n1) + (u64)cneg64(s.a32.v, n2));
-                    c = (i64)((u64)c + (u64)t);
-                    f = (i64)((u64)f + (u64)h + 2ull * (u64)b);
-                    g = (i64)((u64)g + (u64)h + 2ull * (u64)a);
+                    const bool n1 = sg1 != sg3, n2 = sg2 != sg3;
+                    s13 += dflip(s11, n1) + dflip(s12, n2);
+                    s23 += dflip(s21, n1) + dflip(s22, n2);
+                    s33 += dflip(s31, n1) + dflip(s32, n2);
+                    c += sum;
+                    f += h + (b + b);
+                    g += h + (a + a);
                 }
             }
         }
 
-        // -- shear 1: col2 += t col1                               551-567
-        i64 den = (i64)((u64)a << 1);
-        double rden = rcp_f64(__ll2double_rn(den));
+        // shear 1: col2 += t col1                                    551-567
+        const double den = a + a;
+        const double rden = rcp_f64(den);
         {
-            i64 t = shear_t(a, h, den, rden);
-            t = active ? t : 0;
-            const u64 ts = (u64)cneg64(t, sg1 != sg2);
-            s.a12.v = (i64)((u64)s.a12.v + ts * (u64)s.a11.v);
-            s.a22.v = (i64)((u64)s.a22.v + ts * (u64)s.a21.v);
-            s.a32.v = (i64)((u64)s.a32.v + ts * (u64)s.a31.v);
-            const u64 temp = (u64)a * (u64)t;
-            h = (i64)((u64)h + temp);
-            b = (i64)((u64)b + (u64)h * (u64)t);
-            f = (i64)((u64)f + (u64)g * (u64)t);
-            h = (i64)((u64)h + temp);
+            double t = dshear_t(a, h, den, rden);
+            t = active ? t : 0.0;
+            const double ts = dflip(t, sg1 != sg2);
+            s12 = fma(ts, s11, s12); s22 = fma(ts, s21, s22); s32 = fma(ts, s31, s32);
+            const double temp = a * t;
+            h += temp;
+            b = fma(h, t, b);
+            f = fma(g, t, f);
+            h += temp;
         }
-        // -- shear 2: col3 += t col2                               569-585
+        // shear 2: col3 += t col2                                    569-585
         {
-            const i64 den2 = (i64)((u64)b << 1);
-            const double rden2 = rcp_f64(__ll2double_rn(den2));
-            i64 t = shear_t(b, f, den2, rden2);
-            t = active ? t : 0;
-            const u64 ts = (u64)cneg64(t, sg2 != sg3);
-            s.a13.v = (i64)((u64)s.a13.v + ts * (u64)s.a12.v);
-            s.a23.v = (i64)((u64)s.a23.v + ts * (u64)s.a22.v);
-            s.a33.v = (i64)((u64)s.a33.v + ts * (u64)s.a32.v);
-            const u64 temp = (u64)b * (u64)t;
-            f = (i64)((u64)f + temp);
-            c = (i64)((u64)c + (u64)f * (u64)t);
-            g = (i64)((u64)g + (u64)h * (u64)t);
-            f = (i64)((u64)f + temp);
+            const double den2 = b + b;
+            const double rden2 = rcp_f64(den2);
+            double t = dshear_t(b, f, den2, rden2);
+            t = active ? t : 0.0;
+            const double ts = dflip(t, sg2 != sg3);
+            s13 = fma(ts, s12, s13); s23 = fma(ts, s22, s23); s33 = fma(ts, s32, s33);
+            const double temp = b * t;
+            f += temp;
+            c = fma(f, t, c);
+            g = fma(h, t, g);
+            f += temp;
         }
-        // -- shear 3: col3 += t col1   (a, and so 2a, unchanged)    587-603
+        // shear 3: col3 += t col1 (a, hence 2a, is unchanged)         587-603
         {
-            i64 t = shear_t(a, g, den, rden);
-            t = active ? t : 0;
-            const u64 ts = (u64)cneg64(t, sg1 != sg3);
-            s.a13.v = (i64)((u64)s.a13.v + ts * (u64)s.a11.v);
-            s.a23.v = (i64)((u64)s.a23.v + ts * (u64)s.a21.v);
-            s.a33.v = (i64)((u64)s.a33.v + ts * (u64)s.a31.v);
-            const u64 temp = (u64)a * (u64)t;
-            g = (i64)((u64)g + temp);
-            c = (i64)((u64)c + (u64)g * (u64)t);
-            f = (i64)((u64)f + (u64)h * (u64)t);
-            g = (i64)((u64)g + temp);
+            double t = dshear_t(a, g, den, rden);
+            t = active ? t : 0.0;
+            const double ts = dflip(t, sg1 != sg3);
+            s13 = fma(ts, s11, s13); s23 = fma(ts, s21, s23); s33 = fma(ts, s31, s33);
+            const double temp = a * t;
+            g += temp;
+            c = fma(g, t, c);
+            f = fma(h, t, f);
+            g += temp;
         }
 
-        // -- sort a <= b <= c with the reference's tie-breaks      605-624
+        // sort a <= b <= c with the reference's tie-breaks            605-624
         {
-            const bool p = active && (a > b || (a == b && abs_gt(f, g)));
-            cswap64(p, a, b); cswap64(p, f, g);
-            cswap_w(p, s.a11, s.a12); cswap_w(p, s.a21, s.a22); cswap_w(p, s.a31, s.a32);
-            // (c1, c2, c3) <- (-c2, -c1, -c3)
-            const bool o1 = sg1, o2 = sg2;
-            sg1 = p ? !o2 : o1; sg2 = p ? !o1 : o2; sg3 = p ? !sg3 : sg3;
+            const bool p = active && (a > b || (a == b && fabs(f) > fabs(g)));
+            dswap(p, a, b); dswap(p, f, g);
+            dswap(p, s11, s12); dswap(p, s21, s22); dswap(p, s31, s32);
+            const bool o1 = sg1, o2 = sg2;                 // (c1,c2,c3) <- (-c2,-c1,-c3)
+            sg1 = p ? !o2 : o1; sg2 = p ? !o1 : o2; sg3 = sg3 != p;
         }
         {
-            const bool p = active && (b > c || (b == c && abs_gt(g, h)));
-            cswap64(p, b, c); cswap64(p, g, h);
-            cswap_w(p, s.a12, s.a13); cswap_w(p, s.a22, s.a23); cswap_w(p, s.a32, s.a33);
-            // (c1, c2, c3) <- (-c1, -c3, -c2)
-            const bool o2 = sg2, o3 = sg3;
-            sg2 = p ? !o3 : o2; sg3 = p ? !o2 : o3; sg1 = p ? !sg1 : sg1;
+            const bool p = active && (b > c || (b == c && fabs(g) > fabs(h)));
+            dswap(p, b, c); dswap(p, g, h);
+            dswap(p, s12, s13); dswap(p, s22, s23); dswap(p, s32, s33);
+            const bool o2 = sg2, o3 = sg3;                 // (c1,c2,c3) <- (-c1,-c3,-c2)
+            sg2 = p ? !o3 : o2; sg3 = p ? !o2 : o3; sg1 = sg1 != p;
         }
         {
-            const bool p = active && (a > b || (a == b && abs_gt(f, g)));
-            cswap64(p, a, b); cswap64(p, f, g);
-            cswap_w(p, s.a11, s.a12); cswap_w(p, s.a21, s.a22); cswap_w(p, s.a31, s.a32);
+            const bool p = active && (a > b || (a == b && fabs(f) > fabs(g)));
+            dswap(p, a, b); dswap(p, f, g);
+            dswap(p, s11, s12); dswap(p, s21, s22); dswap(p, s31, s32);
             const bool o1 = sg1, o2 = sg2;
-            sg1 = p ? !o2 : o1; sg2 = p ? !o1 : o2; sg3 = p ? !sg3 : sg3;
+            sg1 = p ? !o2 : o1; sg2 = p ? !o1 : o2; sg3 = sg3 != p;
         }
 
-        // -- sign normalisation                                      626-687
+        // sign normalisation                                          626-687
         {
-            const bool fneg = f < 0, gneg = g < 0, hneg = h < 0;
-            const bool fz = f == 0, gz = g == 0, hz = h == 0;
+            const bool fneg = f < 0.0, gneg = g < 0.0, hneg = h < 0.0;
+            const bool fz = f == 0.0, gz = g == 0.0, hz = h == 0.0;
             const bool even_neg = ((int)fneg + (int)gneg + (int)hneg) % 2 == 0;
             const bool fgh = !fz && !gz && !hz && even_neg;
-            bool s1 = !fneg && !fz, s2 = !gneg && !gz, s3 = !hneg && !hz;
-            const bool odd = ((int)s1 + (int)s2 + (int)s3) % 2 == 1;
-            s1 = s1 || (odd && fz);
-            s2 = s2 || (odd && !fz && gz);
-            s3 = s3 || (odd && !fz && !gz && hz);
-            const bool n1 = active && (fgh ? fneg : s1);
-            const bool n2 = active && (fgh ? gneg : s2);
-            const bool n3 = active && (fgh ? hneg : s3);
-            f = cneg64(f, n1); g = cneg64(g, n2); h = cneg64(h, n3);
+            bool p1 = !fneg && !fz, p2 = !gneg && !gz, p3 = !hneg && !hz;
+            const bool odd = ((int)p1 + (int)p2 + (int)p3) % 2 == 1;
+            p1 = p1 || (odd && fz);
+            p2 = p2 || (odd && !fz && gz);
+            p3 = p3 || (odd && !fz && !gz && hz);
+            const bool n1 = active && (fgh ? fneg : p1);
+            const bool n2 = active && (fgh ? gneg : p2);
+            const bool n3 = active && (fgh ? hneg : p3);
+            f = dflip(f, n1); g = dflip(g, n2); h = dflip(h, n3);
             sg1 = sg1 != n1; sg2 = sg2 != n2; sg3 = sg3 != n3;
         }
 
-        // -- exit test                                               689-690
-        const i64 sum = (i64)((u64)a + (u64)b + (u64)f + (u64)g + (u64)h);
-        const bool done = abs_le(f, b) && abs_le(g, a) && abs_le(h, a) && sum >= 0;
+        // exit test                                                   689-690
+        sum = (((a + b) + f) + g) + h;
+        const bool done = fabs(f) <= b && fabs(g) <= a && fabs(h) <= a && sum >= 0.0;
         active = active && !done;
     }
 
-    // materialise the lazy signs
-    s.a11.v = cneg64(s.a11.v, sg1); s.a21.v = cneg64(s.a21.v, sg1); s.a31.v = cneg64(s.a31.v, sg1);
-    s.a12.v = cneg64(s.a12.v, sg2); s.a22.v = cneg64(s.a22.v, sg2); s.a32.v = cneg64(s.a32.v, sg2);
-    s.a13.v = cneg64(s.a13.v, sg3); s.a23.v = cneg64(s.a23.v, sg3); s.a33.v = cneg64(s.a33.v, sg3);
+    d.a = a; d.b = b; d.c = c; d.f = f; d.g = g; d.h = h;
+    d.s11 = dflip(s11, sg1); d.s21 = dflip(s21, sg1); d.s31 = dflip(s31, sg1);
+    d.s12 = dflip(s12, sg2); d.s22 = dflip(s22, sg2); d.s32 = dflip(s32, sg2);
+    d.s13 = dflip(s13, sg3); d.s23 = dflip(s23, sg3); d.s33 = dflip(s33, sg3);
+    return iters;
+}
 
-    // boundary fix-ups, rare: the branchy generic code                693-764
-    W64 A(a), B(b), C(c), F(f), G(g), H(h), t;
-    const W64 zero(0);
-    W64 sum = A + B + F + G + H;
-    if (sum.is_zero() && A.twice() + G.twice() + H > zero)
+// Post-loop boundary fix-ups (QuadForm.h:693-764): rare, so plain branches.
+template <class Z>
+__device__ __forceinline__ void reduce_boundary(Form<Z> &q, Iso<Z> &s)
+{
+    Z a = q.a, b = q.b, c = q.c, f = q.f, g = q.g, h = q.h, t;
+    const Z zero = Z(0);
+    Z sum = a + b + f + g + h;
+    if (sum.is_zero() && a.twice() + g.twice() + h > zero)   // 693-700
     {
         s.fix_sum();
-        C += sum;
-        F += H + B.twice(); F = -F;
-        G += H + A.twice(); G = -G;
+        c += sum;
+        f += h + b.twice(); f = -f;
+        g += h + a.twice(); g = -g;
     }
-    if (A == -H && !G.is_zero()) { s.fix_ah(); F += G; F = -F; G = -G; H = -H; }
-    if (A == -G && !H.is_zero()) { s.fix_ag(); F += H; F = -F; H = -H; G += A.twice(); }
-    if (B == -F && !H.is_zero()) { s.fix_bf(); G += H; G = -G; H = -H; F += B.twice(); }
-    if (A == H && G > F.twice()) { s.edge_ah(); F = G - F; }
-    if (A == G && H > F.twice()) { s.edge_ag(); F = H - F; }
-    if (B == F && H > G.twice()) { s.edge_bf(); G = H - G; }
-    if (A == B && F.abs() > G.abs()) { s.swap12_neg(); t = A; A = B; B = t; t = G; G = F; F = t; }
-    if (B == C && G.abs() > H.abs()) { s.swap23_neg(); t = G; G = H; H = t; }
-    if (A == B && F.abs() > G.abs()) { s.swap12_neg(); t = G; G = F; F = t; }
+    if (a == -h && !g.is_zero()) { s.fix_ah(); f += g; f = -f; g = -g; h = -h; }              // 702-708
+    if (a == -g && !h.is_zero()) { s.fix_ag(); f += h; f = -f; h = -h; g += a.twice(); }      // 710-716
+    if (b == -f && !h.is_zero()) { s.fix_bf(); g += h; g = -g; h = -h; f += b.twice(); }      // 718-724
+    if (a == h && g > f.twice()) { s.edge_ah(); f = g - f; }                                  // 726-730
+    if (a == g && h > f.twice()) { s.edge_ag(); f = h - f; }                                  // 732-736
+    if (b == f && h > g.twice()) { s.edge_bf(); g = h - g; }                                  // 738-742
+    if (a == b && f.abs() > g.abs()) { s.swap12_neg(); t = a; a = b; b = t; t = g; g = f; f = t; }   // 744-750
+    if (b == c && g.abs() > h.abs()) { s.swap23_neg(); t = g; g = h; h = t; }                 // 752-757
+    if (a == b && f.abs() > g.abs()) { s.swap12_neg(); t = g; g = f; f = t; }                 // 759-764
+    q.a = a; q.b = b; q.c = c; q.f = f; q.g = g; q.h = h;
+}
 
-    q.a = A; q.b = B; q.c = C; q.f = F; q.g = G; q.h = H;
-    return true;
+// Reduction entry point of the kernels: FP64 loop when the launch allows it and
+// the whole warp's operands are small, else the integer code.  Every lane of the
+// warp must call this (it votes).
+template <class Z>
+__device__ __forceinline__ bool reduce_neighbor(Form<Z> &q, Iso<Z> &s, bool fp64_allowed)
+{
+    bool small = fits50(q.a) && fits50(q.b) && fits50(q.c) && fits50(q.f) && fits50(q.g) && fits50(q.h) &&
+                 fits50(s.a11) && fits50(s.a12) && fits50(s.a13) && fits50(s.a21) && fits50(s.a22) &&
+                 fits50(s.a23) && fits50(s.a31) && fits50(s.a32) && fits50(s.a33) &&
+                 q.a > Z(0) && q.b > Z(0);
+    __syncwarp(0xffffffffu);
+    if (!(fp64_allowed && __all_sync(0xffffffffu, small))) return eisenstein_reduce(q, s);
+
+    DReduce d;
+    d.a = __ll2double_rn(q.a.low64()); d.b = __ll2double_rn(q.b.low64()); d.c = __ll2double_rn(q.c.low64());
+    d.f = __ll2double_rn(q.f.low64()); d.g = __ll2double_rn(q.g.low64()); d.h = __ll2double_rn(q.h.low64());
+    d.s11 = __ll2double_rn(s.a11.low64()); d.s12 = __ll2double_rn(s.a12.low64()); d.s13 = __ll2double_rn(s.a13.low64());
+    d.s21 = __ll2double_rn(s.a21.low64()); d.s22 = __ll2double_rn(s.a22.low64()); d.s23 = __ll2double_rn(s.a23.low64());
+    d.s31 = __ll2double_rn(s.a31.low64()); d.s32 = __ll2double_rn(s.a32.low64()); d.s33 = __ll2double_rn(s.a33.low64());
+    const int iters = reduce_loop_fp64(d);
+    q.a = Z(__double2ll_rn(d.a)); q.b = Z(__double2ll_rn(d.b)); q.c = Z(__double2ll_rn(d.c));
+    q.f = Z(__double2ll_rn(d.f)); q.g = Z(__double2ll_rn(d.g)); q.h = Z(__double2ll_rn(d.h));
+    s.a11 = Z(__double2ll_rn(d.s11)); s.a12 = Z(__double2ll_rn(d.s12)); s.a13 = Z(__double2ll_rn(d.s13));
+    s.a21 = Z(__double2ll_rn(d.s21)); s.a22 = Z(__double2ll_rn(d.s22)); s.a23 = Z(__double2ll_rn(d.s23));
+    s.a31 = Z(__double2ll_rn(d.s31)); s.a32 = Z(__double2ll_rn(d.s32)); s.a33 = Z(__double2ll_rn(d.s33));
+    reduce_boundary(q, s);
+    return iters <= TB_REDUCE_CAP;
 }
 
 // ---------------------------------------------------------------------------
@@ -901,7 +929,7 @@ __device__ __forceinline__ int one_neighbor(int n, u32 t, const RepPrime &rp, co
         o.s.a21 = zero; o.s.a22 = one; o.s.a23 = zero;
         o.s.a31 = zero; o.s.a32 = zero; o.s.a33 = one;
     }
-    const bool reduced = eisenstein_reduce(o.q, o.s);
+    const bool reduced = reduce_neighbor(o.q, o.s, pc.fp64_reduce != 0);
     if (!built || !reduced) return NBR_OVERFLOW;
 
     const int r = genus_lookup(o.q, gc);                     // Genus.h:575

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -222,6 +223,7 @@ struct tb_genus {
     std::vector<int64_t> primes, conductors, dims, q;
     std::vector<int32_t> lut;
 
+    double lambda_min = 1.0;    // lower bound of the smallest Gram eigenvalue over all representatives
     cudaStream_t stream = 0;
     DevBuf<i64> d_cur, d_rep, d_disc;
     DevBuf<int> d_slots, d_lut;
@@ -322,6 +324,20 @@ static int upload_table(tb_genus *g, const tb_genus_desc *d)
         const u64 a = (u64)c[0], b = (u64)c[1], cc = (u64)c[2], f = (u64)c[3], gg = (u64)c[4], h = (u64)c[5];
         disc[n] = (i64)(a * (4ull * b * cc - f * f) - b * gg * gg + h * (f * gg - cc * h));
     }
+    // lambda_min(Gram) >= det(Gram) / trace(Gram)^2 for a positive definite 3x3 Gram matrix
+    // (det = lambda1 lambda2 lambda3 <= lambda_min * trace^2); det(Gram) = disc / 4
+    double lam = 1e300;
+    bool definite = true;
+    for (int n = 0; n < N; ++n)
+    {
+        const i64 *c = cur + (size_t)n * TB_REC_WORDS;
+        const double a = (double)c[0], b = (double)c[1], cc = (double)c[2], f = (double)c[3], gg = (double)c[4], h = (double)c[5];
+        const double det4 = a * (4.0 * b * cc - f * f) - b * gg * gg + h * (f * gg - cc * h);
+        const double tr = a + b + cc;
+        if (!(a > 0 && b > 0 && cc > 0 && det4 > 0 && 4.0 * a * b - h * h > 0)) { definite = false; break; }
+        lam = std::min(lam, 0.25 * det4 / (tr * tr));
+    }
+    g->lambda_min = definite ? lam * 0.5 : 0.0;   // 0 disables the FP64 reduce loop
     // open-addressing table of representatives: 2 * 2^ceil(log2 N) slots (>= 32), linear probing,
     // keyed by the reference's FNV hash of the six coefficients (HashMap.h:10-24, QuadForm.cpp:779-803).
     for (u32 i = 0; i < slots; ++i) table[i] = -1;
@@ -472,6 +488,9 @@ static int setup_prime(tb_genus *g, uint64_t p)
     pc.dp = make_invdiv(p);
     pc.dpp = make_invdiv(p * p);
     pc.use_lut = (p > 2 && p < (1ull << 22)) ? 1u : 0u;
+    // FP64 reduce loop: isometry entries are bounded by p * sqrt(M / lambda_min) with M < 2^50 the
+    // loop's entry guard on the coefficients (tb_neighbor.cuh); require that bound below 2^52.
+    pc.fp64_reduce = ((double)p * sqrt(1125899906842624.0 / g->lambda_min) < 4503599627370496.0) ? 1u : 0u;
     if (pc.use_lut)
     {
         TB_CUDA(g->d_invlut.reserve(p));
