@@ -36,7 +36,7 @@ struct PrimeCtx {
     u32 p;
     u32 use_lut;
     u32 fp64_reduce;  // host-verified: isometry entries stay below 2^52 in the FP64 reduce loop
-    u32 pad;
+    u32 m32;          // floor(2^32 / p) when p < 2^16 (32-bit Barrett), else 0
     u64 pp;
     InvDiv dp;        // division by p
     InvDiv dpp;       // division by p^2
@@ -53,6 +53,8 @@ struct GenusCtx {
     const i64 *disc;      // [N] wrap-around discriminant of each representative
     const int *slots;     // [slot_mask+1] representative index or -1
     InvDiv spin[TB_MAX_PRIMES];   // the level's prime divisors
+    u64 spin_inv[TB_MAX_PRIMES];  // d^-1 mod 2^64 (0 for d = 2)
+    u64 spin_qmax[TB_MAX_PRIMES]; // floor((2^64 - 1) / d)
 };
 
 template <class Z>
@@ -167,6 +169,13 @@ struct Iso {
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ u32 fp_mul(u32 a, u32 b, const PrimeCtx &pc)
 {
+    if (pc.m32)
+    {
+        // p < 2^16: the product fits 32 bits; Barrett quotient is floor(x/p) or one less
+        const u32 x = a * b;
+        u32 r = x - __umulhi(x, pc.m32) * pc.p;
+        return r >= pc.p ? r - pc.p : r;
+    }
     u64 r;
     udivmod((u64)a * (u64)b, pc.dp, r);
     return (u32)r;
@@ -569,30 +578,41 @@ __device__ __forceinline__ double rcp_f64(double d)
     r = fma(r, e, r);
     return r;
 }
-__device__ __forceinline__ double dflip(double x, bool neg)
+// x with its sign bit XORed by m (m = 0 or 0x80000000): one LOP3
+__device__ __forceinline__ double xflip(double x, u32 m)
 {
-    return __hiloint2double(__double2hiint(x) ^ (neg ? (int)0x80000000 : 0), __double2loint(x));
+    return __hiloint2double(__double2hiint(x) ^ (int)m, __double2loint(x));
 }
-__device__ __forceinline__ void dswap(bool p, double &x, double &y)
+__device__ __forceinline__ double dflip(double x, bool neg) { return xflip(x, neg ? 0x80000000u : 0u); }
+// conditional swap, select form (ALU pipe: 4 FSEL)
+__device__ __forceinline__ void dswap_sel(bool p, double &x, double &y)
 {
     const double t = p ? y : x;
     y = p ? x : y;
     x = t;
 }
-// shear multiplier  t = a >= h ? floor((a-h)/2a) : -floor((a+h-1)/2a)   (QuadForm.h:551-558);
-// num >= 0, den > 0, num/den < 2^50: the rounded estimate is off by at most one.
-__device__ __forceinline__ double dshear_t(double a, double h, double den, double rden)
+// conditional swap, arithmetic form (FP64 pipe: DADD + 2 DFMA), m = 1.0 to swap, 0.0 to keep;
+// exact for integer-valued operands with |y - x| < 2^53
+__device__ __forceinline__ void dswap_fma(double m, double &x, double &y)
 {
-    const bool ge = a >= h;
-    const double num = ge ? __dadd_rn(a, -h) : __dadd_rn(__dadd_rn(a, h), -1.0);
-    const double magic = 4503599627370496.0;   // 2^52
-    double q = __dadd_rn(__dadd_rn(__dmul_rn(num, rden), magic), -magic);
-    double r = fma(-q, den, num);               // exact
-    const bool lo = r < 0.0;
-    q = lo ? q - 1.0 : q;
-    r = lo ? r + den : r;
-    q = r >= den ? q + 1.0 : q;
-    return ge ? q : -q;
+    const double d = y - x;
+    x = fma(m, d, x);
+    y = fma(-m, d, y);
+}
+// The reference's shear multiplier (QuadForm.h:551-558)
+//     t = a >= h ? (a-h) div 2a : -((a+h-1) div 2a)
+// is floor((a-h)/2a) in both branches (for h > a: -ceil((h-a)/2a) = -floor((h-a+2a-1)/2a)).
+// q = RN(num * rden) by the 1.5*2^52 trick is floor or floor+1 (the estimate is within 1/2 of
+// num/den for |num/den| < 2^49); the exact remainder tells which.  `act` = 1.0 or 0.0 freezes
+// finished lanes.
+__device__ __forceinline__ double dshear_t(double a, double h, double den, double rden, double act)
+{
+    const double num = a - h;
+    const double magic = 6755399441055744.0;   // 1.5 * 2^52
+    const double q = __dadd_rn(__fma_rn(num, rden, magic), -magic);
+    const double r = __fma_rn(-q, den, num);    // exact
+    const double corr = __hiloint2double(r < 0.0 ? (int)0xBFF00000 : 0, 0);   // -1.0 or 0.0
+    return (q + corr) * act;
 }
 
 // 2^50 magnitude test on an int64
@@ -612,8 +632,11 @@ __device__ __forceinline__ int reduce_loop_fp64(DReduce &d)
     double a = d.a, b = d.b, c = d.c, f = d.f, g = d.g, h = d.h;
     double s11 = d.s11, s12 = d.s12, s13 = d.s13, s21 = d.s21, s22 = d.s22, s23 = d.s23;
     double s31 = d.s31, s32 = d.s32, s33 = d.s33;
-    bool sg1 = false, sg2 = false, sg3 = false;   // actual column i = (sg_i ? -1 : 1) * stored column i
+    // lazy column signs as sign-bit masks: actual column i = stored column i with its sign XOR sg_i
+    u32 sg1 = 0u, sg2 = 0u, sg3 = 0u;
+    const u32 SIGN = 0x80000000u;
     bool active = true;
+    double act = 1.0;
     int iters = 0;
     const unsigned warp = 0xffffffffu;
     double sum = (((a + b) + f) + g) + h;
@@ -629,10 +652,9 @@ __device__ __forceinline__ int reduce_loop_fp64(DReduce &d)
             {
                 if (fix)
                 {
-                    const bool n1 = sg1 != sg3, n2 = sg2 != sg3;
-                    s13 += dflip(s11, n1) + dflip(s12, n2);
-                    s23 += dflip(s21, n1) + dflip(s22, n2);
-                    s33 += dflip(s31, n1) + dflip(s32, n2);
+                    s13 += xflip(s11, sg1 ^ sg3) + xflip(s12, sg2 ^ sg3);
+                    s23 += xflip(s21, sg1 ^ sg3) + xflip(s22, sg2 ^ sg3);
+                    s33 += xflip(s31, sg1 ^ sg3) + xflip(s32, sg2 ^ sg3);
                     c += sum;
                     f += h + (b + b);
                     g += h + (a + a);
@@ -644,9 +666,8 @@ __device__ __forceinline__ int reduce_loop_fp64(DReduce &d)
         const double den = a + a;
         const double rden = rcp_f64(den);
         {
-            double t = dshear_t(a, h, den, rden);
-            t = active ? t : 0.0;
-            const double ts = dflip(t, sg1 != sg2);
+            const double t = dshear_t(a, h, den, rden, act);
+            const double ts = xflip(t, sg1 ^ sg2);
             s12 = fma(ts, s11, s12); s22 = fma(ts, s21, s22); s32 = fma(ts, s31, s32);
             const double temp = a * t;
             h += temp;
@@ -658,9 +679,8 @@ __device__ __forceinline__ int reduce_loop_fp64(DReduce &d)
         {
             const double den2 = b + b;
             const double rden2 = rcp_f64(den2);
-            double t = dshear_t(b, f, den2, rden2);
-            t = active ? t : 0.0;
-            const double ts = dflip(t, sg2 != sg3);
+            const double t = dshear_t(b, f, den2, rden2, act);
+            const double ts = xflip(t, sg2 ^ sg3);
             s13 = fma(ts, s12, s13); s23 = fma(ts, s22, s23); s33 = fma(ts, s32, s33);
             const double temp = b * t;
             f += temp;
@@ -670,9 +690,8 @@ __device__ __forceinline__ int reduce_loop_fp64(DReduce &d)
         }
         // shear 3: col3 += t col1 (a, hence 2a, is unchanged)         587-603
         {
-            double t = dshear_t(a, g, den, rden);
-            t = active ? t : 0.0;
-            const double ts = dflip(t, sg1 != sg3);
+            const double t = dshear_t(a, g, den, rden, act);
+            const double ts = xflip(t, sg1 ^ sg3);
             s13 = fma(ts, s11, s13); s23 = fma(ts, s21, s23); s33 = fma(ts, s31, s33);
             const double temp = a * t;
             g += temp;
@@ -682,56 +701,62 @@ __device__ __forceinline__ int reduce_loop_fp64(DReduce &d)
         }
 
         // sort a <= b <= c with the reference's tie-breaks            605-624
+        // (form pairs swap by select on the ALU pipe, isometry columns arithmetically on the
+        //  FP64 pipe: the two pipes are the kernel's co-limiters)
         {
             const bool p = active && (a > b || (a == b && fabs(f) > fabs(g)));
-            dswap(p, a, b); dswap(p, f, g);
-            dswap(p, s11, s12); dswap(p, s21, s22); dswap(p, s31, s32);
-            const bool o1 = sg1, o2 = sg2;                 // (c1,c2,c3) <- (-c2,-c1,-c3)
-            sg1 = p ? !o2 : o1; sg2 = p ? !o1 : o2; sg3 = sg3 != p;
+            const double m = p ? 1.0 : 0.0;
+            dswap_sel(p, a, b); dswap_sel(p, f, g);
+            dswap_fma(m, s11, s12); dswap_fma(m, s21, s22); dswap_fma(m, s31, s32);
+            const u32 pm = p ? SIGN : 0u, o1 = sg1;        // (c1,c2,c3) <- (-c2,-c1,-c3)
+            sg1 = (p ? sg2 : sg1) ^ pm; sg2 = (p ? o1 : sg2) ^ pm; sg3 ^= pm;
         }
         {
             const bool p = active && (b > c || (b == c && fabs(g) > fabs(h)));
-            dswap(p, b, c); dswap(p, g, h);
-            dswap(p, s12, s13); dswap(p, s22, s23); dswap(p, s32, s33);
-            const bool o2 = sg2, o3 = sg3;                 // (c1,c2,c3) <- (-c1,-c3,-c2)
-            sg2 = p ? !o3 : o2; sg3 = p ? !o2 : o3; sg1 = sg1 != p;
+            const double m = p ? 1.0 : 0.0;
+            dswap_sel(p, b, c); dswap_sel(p, g, h);
+            dswap_fma(m, s12, s13); dswap_fma(m, s22, s23); dswap_fma(m, s32, s33);
+            const u32 pm = p ? SIGN : 0u, o2 = sg2;        // (c1,c2,c3) <- (-c1,-c3,-c2)
+            sg2 = (p ? sg3 : sg2) ^ pm; sg3 = (p ? o2 : sg3) ^ pm; sg1 ^= pm;
         }
         {
             const bool p = active && (a > b || (a == b && fabs(f) > fabs(g)));
-            dswap(p, a, b); dswap(p, f, g);
-            dswap(p, s11, s12); dswap(p, s21, s22); dswap(p, s31, s32);
-            const bool o1 = sg1, o2 = sg2;
-            sg1 = p ? !o2 : o1; sg2 = p ? !o1 : o2; sg3 = sg3 != p;
+            const double m = p ? 1.0 : 0.0;
+            dswap_sel(p, a, b); dswap_sel(p, f, g);
+            dswap_fma(m, s11, s12); dswap_fma(m, s21, s22); dswap_fma(m, s31, s32);
+            const u32 pm = p ? SIGN : 0u, o1 = sg1;
+            sg1 = (p ? sg2 : sg1) ^ pm; sg2 = (p ? o1 : sg2) ^ pm; sg3 ^= pm;
         }
 
         // sign normalisation                                          626-687
         {
             const bool fneg = f < 0.0, gneg = g < 0.0, hneg = h < 0.0;
             const bool fz = f == 0.0, gz = g == 0.0, hz = h == 0.0;
-            const bool even_neg = ((int)fneg + (int)gneg + (int)hneg) % 2 == 0;
+            const bool even_neg = !((fneg != gneg) != hneg);
             const bool fgh = !fz && !gz && !hz && even_neg;
             bool p1 = !fneg && !fz, p2 = !gneg && !gz, p3 = !hneg && !hz;
-            const bool odd = ((int)p1 + (int)p2 + (int)p3) % 2 == 1;
+            const bool odd = (p1 != p2) != p3;
             p1 = p1 || (odd && fz);
             p2 = p2 || (odd && !fz && gz);
             p3 = p3 || (odd && !fz && !gz && hz);
-            const bool n1 = active && (fgh ? fneg : p1);
-            const bool n2 = active && (fgh ? gneg : p2);
-            const bool n3 = active && (fgh ? hneg : p3);
-            f = dflip(f, n1); g = dflip(g, n2); h = dflip(h, n3);
-            sg1 = sg1 != n1; sg2 = sg2 != n2; sg3 = sg3 != n3;
+            const u32 n1 = (active && (fgh ? fneg : p1)) ? SIGN : 0u;
+            const u32 n2 = (active && (fgh ? gneg : p2)) ? SIGN : 0u;
+            const u32 n3 = (active && (fgh ? hneg : p3)) ? SIGN : 0u;
+            f = xflip(f, n1); g = xflip(g, n2); h = xflip(h, n3);
+            sg1 ^= n1; sg2 ^= n2; sg3 ^= n3;
         }
 
         // exit test                                                   689-690
         sum = (((a + b) + f) + g) + h;
         const bool done = fabs(f) <= b && fabs(g) <= a && fabs(h) <= a && sum >= 0.0;
         active = active && !done;
+        act = active ? 1.0 : 0.0;
     }
 
     d.a = a; d.b = b; d.c = c; d.f = f; d.g = g; d.h = h;
-    d.s11 = dflip(s11, sg1); d.s21 = dflip(s21, sg1); d.s31 = dflip(s31, sg1);
-    d.s12 = dflip(s12, sg2); d.s22 = dflip(s22, sg2); d.s32 = dflip(s32, sg2);
-    d.s13 = dflip(s13, sg3); d.s23 = dflip(s23, sg3); d.s33 = dflip(s33, sg3);
+    d.s11 = xflip(s11, sg1); d.s21 = xflip(s21, sg1); d.s31 = xflip(s31, sg1);
+    d.s12 = xflip(s12, sg2); d.s22 = xflip(s22, sg2); d.s32 = xflip(s32, sg2);
+    d.s13 = xflip(s13, sg3); d.s23 = xflip(s23, sg3); d.s33 = xflip(s33, sg3);
     return iters;
 }
 
@@ -826,11 +851,46 @@ __device__ __forceinline__ int genus_lookup(const Form<Z> &q, const GenusCtx &gc
 // Spinor norm class.  Spinor::compute_vals (Spinor.h:52-66) and Spinor::norm
 // (Spinor.h:19-41).
 // ---------------------------------------------------------------------------
+// Parity of the d-adic valuation of a nonzero 64-bit magnitude, d an odd prime:
+// d | y  <=>  y * d^-1 (mod 2^64) <= floor((2^64-1)/d), and then that product is y / d.
+__device__ __forceinline__ u32 parities_u64(u64 y, const GenusCtx &gc)
+{
+    u32 val = 0;
+    for (int i = 0; i < gc.K; ++i)
+    {
+        const u64 dinv = gc.spin_inv[i];
+        u32 odd;
+        if (dinv == 0)
+        {
+            odd = (u32)__ffsll((i64)y) - 1u;          // d = 2: trailing zeros
+        }
+        else
+        {
+            const u64 qmax = gc.spin_qmax[i];
+            odd = 0;
+            u64 q = y * dinv;
+            while (q <= qmax) { y = q; odd ^= 1u; q = y * dinv; }
+        }
+        val |= (odd & 1u) << i;
+    }
+    return val;
+}
+__device__ __forceinline__ u32 prime_parities(W64 x, const GenusCtx &gc)
+{
+    if (x.is_zero()) { raise_overflow(); return 0; }   // the reference's loop would not terminate
+    return parities_u64(x.umag(), gc);
+}
+
 template <class Z>
 __device__ __forceinline__ u32 prime_parities(Z x, const GenusCtx &gc)
 {
     u32 val = 0;
     if (x.is_zero()) { raise_overflow(); return 0; }   // the reference's loop would not terminate
+    {
+        u64 mh, ml;
+        x.umag(mh, ml);
+        if (mh == 0) return parities_u64(ml, gc);
+    }
     for (int i = 0; i < gc.K; ++i)
     {
         const InvDiv &iv = gc.spin[i];
@@ -938,22 +998,37 @@ __device__ __forceinline__ int one_neighbor(int n, u32 t, const RepPrime &rp, co
     o.composed = false;
 
     const Z pz = Z((i64)pc.p);
-    if (r != n || want_comp)                                 // Genus.h:588-615
+    if (r == n && !want_comp)                                // Genus.h:582-585
     {
-        const i64 *rep = gc.rep + (size_t)r * TB_REC_WORDS;
-        Iso<Z> cs = load_iso<Z>(cur + 7);
-        Iso<Z> rsinv = load_iso<Z>(rep + 7);
-        o.comp = iso_mul(iso_mul(cs, o.s), rsinv);
-        o.denom = pz * Z(__ldg(cur + 6)) * Z(__ldg(rep + 6));
-        o.composed = true;
+        o.spin = spinor_norm(o.q, o.s, pz, gc);
+        return NBR_OK;
     }
-    if (r == n)                                              // Genus.h:582-585
+    const i64 *rep = gc.rep + (size_t)r * TB_REC_WORDS;      // Genus.h:588-615
+    const Iso<Z> cs = load_iso<Z>(cur + 7);
+    const Iso<Z> rsinv = load_iso<Z>(rep + 7);
+    const Iso<Z> m = iso_mul(cs, o.s);
+    o.denom = pz * Z(__ldg(cur + 6)) * Z(__ldg(rep + 6));
+    if (!want_comp)
+    {
+        // Spinor::norm's first case needs only the trace of cur.s * s * rep.sinv
+        const Z tr = m.a11 * rsinv.a11 + m.a12 * rsinv.a21 + m.a13 * rsinv.a31 +
+                     m.a21 * rsinv.a12 + m.a22 * rsinv.a22 + m.a23 * rsinv.a32 +
+                     m.a31 * rsinv.a13 + m.a32 * rsinv.a23 + m.a33 * rsinv.a33;
+        if (tr != -o.denom)                                  // Spinor.h:21-25
+        {
+            o.spin = prime_parities(tr + o.denom, gc);
+            return NBR_OK;
+        }
+    }
+    o.comp = iso_mul(m, rsinv);
+    o.composed = true;
+    if (r == n)
     {
         o.spin = spinor_norm(o.q, o.s, pz, gc);
     }
     else
     {
-        Form<Z> mother = load_form<Z>(gc.rep);
+        const Form<Z> mother = load_form<Z>(gc.rep);
         o.spin = spinor_norm(mother, o.comp, o.denom, gc);
     }
     return NBR_OK;

@@ -366,7 +366,19 @@ static int upload_table(tb_genus *g, const tb_genus_desc *d)
     memset(&gc, 0, sizeof(gc));
     gc.N = N; gc.K = K; gc.slot_mask = slots - 1;
     gc.cur = g->d_cur.ptr; gc.rep = g->d_rep.ptr; gc.disc = g->d_disc.ptr; gc.slots = g->d_slots.ptr;
-    for (int i = 0; i < K; ++i) gc.spin[i] = make_invdiv((u64)d->primes[i]);
+    for (int i = 0; i < K; ++i)
+    {
+        const u64 dd = (u64)d->primes[i];
+        gc.spin[i] = make_invdiv(dd);
+        gc.spin_qmax[i] = ~0ull / dd;
+        u64 inv = 0;
+        if (dd & 1ull)
+        {
+            inv = dd;                                   // Newton: 3 correct bits, doubling each step
+            for (int it = 0; it < 6; ++it) inv *= 2ull - dd * inv;
+        }
+        gc.spin_inv[i] = inv;
+    }
     return TB_OK;
 }
 
@@ -488,6 +500,7 @@ static int setup_prime(tb_genus *g, uint64_t p)
     pc.dp = make_invdiv(p);
     pc.dpp = make_invdiv(p * p);
     pc.use_lut = (p > 2 && p < (1ull << 22)) ? 1u : 0u;
+    pc.m32 = (p > 2 && p < (1ull << 16)) ? (u32)((1ull << 32) / p) : 0u;
     // FP64 reduce loop: isometry entries are bounded by p * sqrt(M / lambda_min) with M < 2^50 the
     // loop's entry guard on the coefficients (tb_neighbor.cuh); require that bound below 2^52.
     pc.fp64_reduce = ((double)p * sqrt(1125899906842624.0 / g->lambda_min) < 4503599627370496.0) ? 1u : 0u;
