@@ -221,7 +221,7 @@ template <bool FILL>
 __global__ void rows_kernel(const __grid_constant__ RowLaunch L)
 {
     extern __shared__ u32 smem[];
-    // layout: mask[mw] | wprefix[mw] | start[maxcols+1] | colr[maxcols] | warp_sums[33] | spins (u16)[P1]
+    // layout: mask[mw] | wprefix[mw] | start[maxcols+1] | colr[maxcols] | scratch[256] | spins (u16)[P1]
     const int mw = L.mask_words;
     const int maxcols = min((int)L.P1, L.N);
     u32 *mask = smem;
@@ -229,7 +229,7 @@ __global__ void rows_kernel(const __grid_constant__ RowLaunch L)
     int *start = (int *)(wprefix + mw);
     int *colr = start + maxcols + 1;
     int *warp_sums = colr + maxcols;
-    unsigned short *spins = (unsigned short *)(warp_sums + 36);
+    unsigned short *spins = (unsigned short *)(warp_sums + 256);
 
     const int lrow = blockIdx.x;
     const int n = L.rep_begin + lrow;
@@ -311,45 +311,109 @@ __global__ void rows_kernel(const __grid_constant__ RowLaunch L)
     // now start[j+1] == begin of run j; the end of run j is the begin of run j+1, nvalid for the last
     // (start[0] is unused by the scatter and still 0)
 
+    // ---- per-conductor row entries, ascending columns, zeros dropped ----------
+    // Each warp owns a contiguous block of columns, so ordered compaction needs no
+    // block-wide scan per tile: warps count their nonzeros with ballots, one sync
+    // combines the per-warp totals, and (FILL) a second sweep writes at the offsets.
+    // Conductors are handled eight at a time (counters live in registers).
     const int C = 1 << L.K;
-    for (int k = 0; k < C; ++k)
-    {
-        const int *lut = L.lut + (size_t)k * L.N;
-        const int npos = lut[n];
-        if (npos == -1) continue;                    // Genus.h:624-625
-        const int out_row = npos - L.rowfirst[k];
-        int *indptr = L.indptr_all + L.rowbase[k];
-        i64 wbase = 0;
-        if (FILL) wbase = L.nnzbase[k] + indptr[out_row];
+    const int lane = tid & 31, w = tid >> 5, nw = nt >> 5;
+    const int B = (((ncols + nw - 1) / nw) + 31) & ~31;       // columns per warp, multiple of 32
+    const int jbeg = min(ncols, w * B), jend = min(ncols, jbeg + B);
+    int *warp_cnt = warp_sums;                                 // [8][32], reuses the scan scratch
+    __shared__ int s_npos[8];
 
-        int row_total = 0;
-        for (int base = 0; base < ncols; base += nt)
+    for (int kc = 0; kc < C; kc += 8)
+    {
+        const int nk = min(8, C - kc);
+        __syncthreads();
+        if (tid < 8) s_npos[tid] = tid < nk ? L.lut[(size_t)(kc + tid) * L.N + n] : -1;
+        __syncthreads();
+
+        int cnt[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) cnt[kk] = 0;
+
+        for (int pass = 0; pass < (FILL ? 2 : 1); ++pass)
         {
-            const int j = base + tid;
-            int value = 0, rpos = -1;
-            if (j < ncols)
+            i64 wbase[8];
+            if (pass == 1)
             {
-                rpos = lut[colr[j]];
-                if (rpos != -1)
+                // exclusive prefix of the per-warp totals -> this warp's first output slot per conductor
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
                 {
-                    const int b = start[j + 1];
-                    const int e = (j + 1 < ncols) ? start[j + 2] : nvalid;
-                    int odd = 0;
-                    for (int i = b; i < e; ++i) odd += __popc((u32)spins[i] & (u32)k) & 1;
-                    value = (e - b) - 2 * odd;
+                    int before = 0;
+                    for (int ww = 0; ww < w; ++ww) before += warp_cnt[kk * 32 + ww];
+                    wbase[kk] = 0;
+                    if (kk < nk && s_npos[kk] != -1)
+                    {
+                        const int k = kc + kk;
+                        const int out_row = s_npos[kk] - L.rowfirst[k];
+                        wbase[kk] = L.nnzbase[k] + (L.indptr_all + L.rowbase[k])[out_row] + before;
+                    }
+                    cnt[kk] = 0;
                 }
             }
-            const int flag = value != 0;
-            int total;
-            const int ex = block_exclusive_scan(flag, warp_sums, total);
-            if (FILL && flag)
+            for (int j0 = jbeg; j0 < jend; j0 += 32)
             {
-                L.data[wbase + row_total + ex] = value;
-                L.indices[wbase + row_total + ex] = rpos;
+                const int j = j0 + lane;
+                const bool valid = j < jend;
+                int r = 0, b = 0, e = 0;
+                if (valid)
+                {
+                    r = colr[j];
+                    b = start[j + 1];
+                    e = (j + 1 < ncols) ? start[j + 2] : nvalid;
+                }
+                // odd[kk] = #{entries of the run with chi_k = -1}
+                int odd[8];
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) odd[kk] = 0;
+                for (int i = b; i < e; ++i)
+                {
+                    const u32 sp = spins[i];
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) odd[kk] += __popc(sp & (u32)(kc + kk)) & 1;
+                }
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                {
+                    if (kk >= nk || s_npos[kk] == -1) continue;          // Genus.h:624-625 (warp-uniform)
+                    const int k = kc + kk;
+                    int value = 0, rpos = -1;
+                    if (valid)
+                    {
+                        rpos = __ldg(L.lut + (size_t)k * L.N + r);
+                        if (rpos != -1) value = (e - b) - 2 * odd[kk];
+                    }
+                    const unsigned ballot = __ballot_sync(0xffffffffu, value != 0);
+                    if (pass == 1 && value != 0)
+                    {
+                        const i64 at = wbase[kk] + cnt[kk] + __popc(ballot & ((1u << lane) - 1u));
+                        L.data[at] = value;
+                        L.indices[at] = rpos;
+                    }
+                    cnt[kk] += __popc(ballot);
+                }
             }
-            row_total += total;
+            if (pass == 0)
+            {
+                if (lane == 0)
+                {
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) warp_cnt[kk * 32 + w] = cnt[kk];
+                }
+                __syncthreads();
+                if (!FILL && tid < nk && s_npos[tid] != -1)
+                {
+                    const int k = kc + tid;
+                    int total = 0;
+                    for (int ww = 0; ww < nw; ++ww) total += warp_cnt[tid * 32 + ww];
+                    (L.indptr_all + L.rowbase[k])[s_npos[tid] - L.rowfirst[k] + 1] = total;
+                }
+            }
         }
-        if (!FILL && tid == 0) indptr[out_row + 1] = row_total;
     }
 }
 

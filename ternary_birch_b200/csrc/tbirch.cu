@@ -603,7 +603,7 @@ static size_t rows_smem_bytes(int N, u32 P1)
 {
     const size_t mw = (N + 31) / 32;
     const size_t maxcols = std::min<size_t>(P1, N);
-    size_t b = (2 * mw + (maxcols + 1) + maxcols + 36) * 4 + (size_t)P1 * 2;
+    size_t b = (2 * mw + (maxcols + 1) + maxcols + 256) * 4 + (size_t)P1 * 2;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -675,6 +675,8 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     int threads = (int)std::min<u32>(512, std::max<u32>(64, (P1 + 31) / 32 * 32));
     TB_CUDA(cudaFuncSetAttribute(rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TB_CUDA(cudaFuncSetAttribute(rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TB_CUDA(cudaFuncSetAttribute(rows_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    TB_CUDA(cudaFuncSetAttribute(rows_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     rows_kernel<false><<<rows, threads, smem, g->stream>>>(R);
     ++g_launches;
     TB_CUDA(cudaGetLastError());
