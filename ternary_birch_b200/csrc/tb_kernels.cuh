@@ -218,7 +218,7 @@ struct RowLaunch {
 };
 
 template <bool FILL>
-__global__ void rows_kernel(const __grid_constant__ RowLaunch L)
+__global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ RowLaunch L)
 {
     extern __shared__ u32 smem[];
     // layout: mask[mw] | wprefix[mw] | start[maxcols+1] | colr[maxcols] | scratch[256] | spins (u16)[P1]
