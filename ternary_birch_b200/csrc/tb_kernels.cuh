@@ -150,9 +150,9 @@ neighbors_kernel(const __grid_constant__ GenusCtx gc, const __grid_constant__ Pr
         }
     }
 
-    __syncthreads();
-    if (threadIdx.x == 0 && *cta_flag_ptr())
-        atomicMin(L.err + 0, (u64)blockIdx.x * TB_NBR_THREADS);
+    // no closing barrier (it held every warp of the CTA until the slowest one finished): a
+    // thread that raised the sticky flag sees its own write, so it reports it itself
+    if (*cta_flag_ptr()) atomicMin(L.err + 0, (u64)blockIdx.x * TB_NBR_THREADS);
 }
 
 // ---------------------------------------------------------------------------

@@ -822,9 +822,8 @@ __device__ __forceinline__ bool reduce_neighbor(Form<Z> &q, Iso<Z> &s, bool fp64
 template <class Z>
 __device__ __forceinline__ int genus_lookup(const Form<Z> &q, const GenusCtx &gc)
 {
-    if (!(q.a.fits_i64() && q.b.fits_i64() && q.c.fits_i64() &&
-          q.f.fits_i64() && q.g.fits_i64() && q.h.fits_i64()))
-        return -1;
+    const bool narrow = q.a.fits_i64() && q.b.fits_i64() && q.c.fits_i64() &&
+                        q.f.fits_i64() && q.g.fits_i64() && q.h.fits_i64();
     const i64 k0 = q.a.low64(), k1 = q.b.low64(), k2 = q.c.low64();
     const i64 k3 = q.f.low64(), k4 = q.g.low64(), k5 = q.h.low64();
     u64 fnv = 0x811c9dc5ull;
@@ -835,16 +834,20 @@ __device__ __forceinline__ int genus_lookup(const Form<Z> &q, const GenusCtx &gc
     fnv = (fnv ^ (u64)k4) * 0x01000193ull;
     fnv = (fnv ^ (u64)k5) * 0x01000193ull;
     u32 slot = (u32)fnv & gc.slot_mask;
-    for (u32 probes = 0; probes <= gc.slot_mask; ++probes)
+    int found = -1;
+    // single exit, so the warp reconverges right after the probe loop (avg 1.3 probes);
+    // every lane of the warp calls this
+    for (u32 probes = 0; narrow && probes <= gc.slot_mask; ++probes)
     {
-        int idx = __ldg(gc.slots + slot);
-        if (idx < 0) return -1;
+        const int idx = __ldg(gc.slots + slot);
+        if (idx < 0) break;
         const longlong2 *key = reinterpret_cast<const longlong2 *>(gc.rep + (size_t)idx * TB_REC_WORDS);
-        longlong2 x = __ldg(key), y = __ldg(key + 1), z = __ldg(key + 2);
-        if (x.x == k0 && x.y == k1 && y.x == k2 && y.y == k3 && z.x == k4 && z.y == k5) return idx;
+        const longlong2 x = __ldg(key), y = __ldg(key + 1), z = __ldg(key + 2);
+        if (x.x == k0 && x.y == k1 && y.x == k2 && y.y == k3 && z.x == k4 && z.y == k5) { found = idx; break; }
         slot = (slot + 1) & gc.slot_mask;
     }
-    return -1;
+    __syncwarp(0xffffffffu);
+    return found;
 }
 
 // ---------------------------------------------------------------------------
@@ -869,7 +872,7 @@ __device__ __forceinline__ u32 parities_u64(u64 y, const GenusCtx &gc)
             const u64 qmax = gc.spin_qmax[i];
             odd = 0;
             u64 q = y * dinv;
-            while (q <= qmax) { y = q; odd ^= 1u; q = y * dinv; }
+            while (q <= qmax) { y = q; odd ^= 1u; q = y * dinv; }   // valuation is 0 for most inputs
         }
         val |= (odd & 1u) << i;
     }
@@ -975,25 +978,31 @@ template <class Z>
 __device__ __forceinline__ int one_neighbor(int n, u32 t, const RepPrime &rp, const PrimeCtx &pc,
                                             const GenusCtx &gc, bool want_comp, Neighbor<Z> &o)
 {
+    // Straight-line: every lane of the warp runs every phase (the reduce loop and the lookup
+    // vote / resynchronise warp-wide).  A lane whose neighbor overflowed carries the
+    // representative's own, already reduced, form through the remaining phases and only its
+    // status differs.
+    int status = NBR_OK;
     const i64 *cur = gc.cur + (size_t)n * TB_REC_WORDS;
-    Form<Z> q = load_form<Z>(cur);
+    const Form<Z> q = load_form<Z>(cur);
     line_for_t(rp, t, pc, o.vx, o.vy, o.vz);
-    const bool built = build_neighbor(q, o.vx, o.vy, o.vz, __ldg(gc.disc + n), pc, o.q, o.s);
-    if (!built)
+    if (!build_neighbor(q, o.vx, o.vy, o.vz, __ldg(gc.disc + n), pc, o.q, o.s))
     {
-        // keep the lane in step with its warp (the W64 reduce votes warp-wide): reduce the
-        // representative's own, already reduced, form; the result is discarded
+        status = NBR_OVERFLOW;
         const Z zero = Z(0), one = Z(1);
         o.q = q;
         o.s.a11 = one; o.s.a12 = zero; o.s.a13 = zero;
         o.s.a21 = zero; o.s.a22 = one; o.s.a23 = zero;
         o.s.a31 = zero; o.s.a32 = zero; o.s.a33 = one;
     }
-    const bool reduced = reduce_neighbor(o.q, o.s, pc.fp64_reduce != 0);
-    if (!built || !reduced) return NBR_OVERFLOW;
+    if (!reduce_neighbor(o.q, o.s, pc.fp64_reduce != 0)) status = NBR_OVERFLOW;
 
-    const int r = genus_lookup(o.q, gc);                     // Genus.h:575
-    if (r < 0) return NBR_NOT_FOUND;
+    int r = genus_lookup(o.q, gc);                           // Genus.h:575
+    if (r < 0)
+    {
+        if (status == NBR_OK) status = NBR_NOT_FOUND;
+        r = n;
+    }
     o.r = r;
     o.composed = false;
 
@@ -1001,7 +1010,7 @@ __device__ __forceinline__ int one_neighbor(int n, u32 t, const RepPrime &rp, co
     if (r == n && !want_comp)                                // Genus.h:582-585
     {
         o.spin = spinor_norm(o.q, o.s, pz, gc);
-        return NBR_OK;
+        return status;
     }
     const i64 *rep = gc.rep + (size_t)r * TB_REC_WORDS;      // Genus.h:588-615
     const Iso<Z> cs = load_iso<Z>(cur + 7);
@@ -1017,7 +1026,7 @@ __device__ __forceinline__ int one_neighbor(int n, u32 t, const RepPrime &rp, co
         if (tr != -o.denom)                                  // Spinor.h:21-25
         {
             o.spin = prime_parities(tr + o.denom, gc);
-            return NBR_OK;
+            return status;
         }
     }
     o.comp = iso_mul(m, rsinv);
@@ -1031,7 +1040,7 @@ __device__ __forceinline__ int one_neighbor(int n, u32 t, const RepPrime &rp, co
         const Form<Z> mother = load_form<Z>(gc.rep);
         o.spin = spinor_norm(mother, o.comp, o.denom, gc);
     }
-    return NBR_OK;
+    return status;
 }
 
 }  // namespace tb
