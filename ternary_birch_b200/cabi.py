@@ -10,7 +10,9 @@ from __future__ import annotations
 import ctypes
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libtbirch.so"
+import os
+
+LIB_PATH = Path(os.environ.get("TBIRCH_LIB", Path(__file__).resolve().parent / "libtbirch.so"))
 
 TB_OK, TB_ERR_INVALID_ARGUMENT, TB_ERR_OVERFLOW, TB_ERR_DOMAIN, TB_ERR_RUNTIME = range(5)
 

@@ -18,6 +18,9 @@
 namespace tb {
 
 #define TB_NBR_THREADS 128
+#ifndef TB_NBR_MINBLOCKS
+#define TB_NBR_MINBLOCKS 7
+#endif
 
 // ---------------------------------------------------------------------------
 // Inverse table mod p (one launch per prime).
@@ -87,7 +90,7 @@ struct NbrLaunch {
 };
 
 template <class Z, int MODE>
-__global__ void __launch_bounds__(TB_NBR_THREADS)
+__global__ void __launch_bounds__(TB_NBR_THREADS, TB_NBR_MINBLOCKS)
 neighbors_kernel(const __grid_constant__ GenusCtx gc, const __grid_constant__ PrimeCtx pc,
                  const __grid_constant__ NbrLaunch L)
 {
@@ -209,6 +212,7 @@ struct RowLaunch {
     int mask_words;        // ceil(N / 32)
     const u32 *W;          // [rows][P1]
     const int *lut;        // [2^K][N]
+    const int *lutT;       // [N][2^K] (transposed: one sector serves all conductors of a column)
     const int *rowbase;    // [2^K] offset of conductor k's indptr block in indptr_all
     const int *rowfirst;   // [2^K] lut[k][first included rep >= rep_begin] (row index of the shard's first row)
     int *indptr_all;       // concatenated (rows_k + 1) blocks
@@ -376,17 +380,33 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) odd[kk] += __popc(sp & (u32)(kc + kk)) & 1;
                 }
+                // row positions of this column for the eight conductors: 32 contiguous bytes
+                int rp[8];
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) rp[kk] = -1;
+                if (valid)
+                {
+                    const int *src = L.lutT + ((size_t)r << L.K) + kc;
+                    if (nk == 8)
+                    {
+                        const int4 x = __ldg(reinterpret_cast<const int4 *>(src));
+                        const int4 y = __ldg(reinterpret_cast<const int4 *>(src) + 1);
+                        rp[0] = x.x; rp[1] = x.y; rp[2] = x.z; rp[3] = x.w;
+                        rp[4] = y.x; rp[5] = y.y; rp[6] = y.z; rp[7] = y.w;
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) if (kk < nk) rp[kk] = __ldg(src + kk);
+                    }
+                }
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk)
                 {
                     if (kk >= nk || s_npos[kk] == -1) continue;          // Genus.h:624-625 (warp-uniform)
-                    const int k = kc + kk;
-                    int value = 0, rpos = -1;
-                    if (valid)
-                    {
-                        rpos = __ldg(L.lut + (size_t)k * L.N + r);
-                        if (rpos != -1) value = (e - b) - 2 * odd[kk];
-                    }
+                    int value = 0;
+                    const int rpos = rp[kk];
+                    if (rpos != -1) value = (e - b) - 2 * odd[kk];
                     const unsigned ballot = __ballot_sync(0xffffffffu, value != 0);
                     if (pass == 1 && value != 0)
                     {

@@ -226,7 +226,7 @@ struct tb_genus {
     double lambda_min = 1.0;    // lower bound of the smallest Gram eigenvalue over all representatives
     cudaStream_t stream = 0;
     DevBuf<i64> d_cur, d_rep, d_disc;
-    DevBuf<int> d_slots, d_lut;
+    DevBuf<int> d_slots, d_lut, d_lutT;
     GenusCtx gc;
 
     // per-prime state (valid for cur_p)
@@ -300,7 +300,7 @@ static int upload_table(tb_genus *g, const tb_genus_desc *d)
     const size_t disc_bytes = (size_t)N * sizeof(i64);
     const size_t slot_bytes = (size_t)slots * sizeof(int);
     const size_t lut_bytes = ((size_t)N << K) * sizeof(int);
-    const size_t total = 2 * rec_bytes + disc_bytes + slot_bytes + lut_bytes;
+    const size_t total = 2 * rec_bytes + disc_bytes + slot_bytes + 2 * lut_bytes;
     if (total > g->h_table_bytes)
     {
         if (g->h_table) cudaFreeHost(g->h_table);
@@ -350,11 +350,16 @@ static int upload_table(tb_genus *g, const tb_genus_desc *d)
         table[s] = n;
     }
     memcpy(lut, d->lut, lut_bytes);
+    int *lutT = lut + ((size_t)N << K);
+    for (int k = 0; k < (1 << K); ++k)
+        for (int n = 0; n < N; ++n) lutT[((size_t)n << K) + k] = d->lut[(size_t)k * N + n];
     TB_CUDA(g->d_cur.reserve((size_t)N * TB_REC_WORDS));
     TB_CUDA(g->d_rep.reserve((size_t)N * TB_REC_WORDS));
     TB_CUDA(g->d_disc.reserve(N));
     TB_CUDA(g->d_slots.reserve(slots));
     TB_CUDA(g->d_lut.reserve((size_t)N << K));
+    TB_CUDA(g->d_lutT.reserve((size_t)N << K));
+    TB_CUDA(cudaMemcpyAsync(g->d_lutT.ptr, lutT, lut_bytes, cudaMemcpyHostToDevice, g->stream));
     TB_CUDA(cudaMemcpyAsync(g->d_cur.ptr, cur, rec_bytes, cudaMemcpyHostToDevice, g->stream));
     TB_CUDA(cudaMemcpyAsync(g->d_rep.ptr, rep, rec_bytes, cudaMemcpyHostToDevice, g->stream));
     TB_CUDA(cudaMemcpyAsync(g->d_disc.ptr, disc, disc_bytes, cudaMemcpyHostToDevice, g->stream));
@@ -442,7 +447,7 @@ extern "C" int tb_genus_upload(tb_genus *g, const tb_genus_desc *d)
 extern "C" void tb_genus_destroy(tb_genus *g)
 {
     if (!g) return;
-    g->d_cur.release(); g->d_rep.release(); g->d_disc.release(); g->d_slots.release(); g->d_lut.release();
+    g->d_cur.release(); g->d_rep.release(); g->d_disc.release(); g->d_slots.release(); g->d_lut.release(); g->d_lutT.release();
     g->d_invlut.release(); g->d_base.release(); g->d_W.release(); g->d_rp.release(); g->d_err.release();
     g->d_tab.release(); g->d_nnz.release();
     if (g->h_err) cudaFreeHost(g->h_err);
@@ -663,7 +668,7 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     RowLaunch R;
     memset(&R, 0, sizeof(R));
     R.N = N; R.K = K; R.rep_begin = rb; R.rows = rows; R.P1 = P1; R.mask_words = (N + 31) / 32;
-    R.W = g->d_W.ptr; R.lut = g->d_lut.ptr;
+    R.W = g->d_W.ptr; R.lut = g->d_lut.ptr; R.lutT = g->d_lutT.ptr;
     R.rowbase = d_tab.ptr; R.rowfirst = d_tab.ptr + C;
     R.indptr_all = h->d_indptr.ptr;
     R.nnzbase = d_nnz.ptr + C;
