@@ -311,14 +311,20 @@ def main():
     # ---- final integer gather of the Hecke rows (once, untimed region) -------
     gather_ms = None
     if world > 1:
-        local = g.hecke_matrix_sparse(p)
+        res = g.hecke_device(p)
         torch.cuda.synchronize()
+        dist.barrier()
         t0 = time.perf_counter()
-        got = shard.gather_csr(local, device=dev)
+        got = shard.gather_hecke_device(res, dev)
         torch.cuda.synchronize()
         gather_ms = (time.perf_counter() - t0) * 1e3
         if rank == 0:
-            assert len(got) == world and all(len(x) == C for x in got)
+            headers, payloads = got
+            assert len(payloads) == world and all(int(h[0]) == C for h in headers)
+            # rank 0's own rows must come back unchanged: conductor-1 data sums to (p+1) * dim
+            nnz0 = int(headers[0][2])
+            assert int(payloads[0][:nnz0].sum().item()) == (p + 1) * N
+        res.close()
 
     # ---- roofline of the dominant kernel (neighbors_kernel) ------------------
     peak = None

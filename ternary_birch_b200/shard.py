@@ -104,3 +104,47 @@ def gather_csr(local: dict, device=None, group=None, dst: int = 0):
         nh, npay = int(all_sizes[r][0]), int(all_sizes[r][1])
         out.append(unpack_csr(hs[r][:nh].cpu().numpy(), ps[r][:npay].cpu().numpy()))
     return out
+
+
+def gather_hecke_device(result, device, group=None, dst: int = 0):
+    """Final integer gather of device-resident Hecke rows (a `HeckeResult`) to rank `dst`.
+
+    Each rank lays its CSR arrays out in ONE int32 device tensor (copied device-to-device out
+    of the library's buffers), the tensors are padded to the largest rank and gathered over
+    NCCL/NVLink.  Returns on dst: (headers, payloads) with headers[r] = int64 [C, then per
+    conductor: conductor, nnz, rows+1] and payloads[r] an int32 device tensor holding, per
+    conductor, data | indices | indptr; None elsewhere.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    C = result.num_conductors()
+    header = [C]
+    total = 0
+    for k in range(C):
+        rows, _, nnz = result.shape(k)
+        header += [result.conductor(k), nnz, rows + 1]
+        total += 2 * nnz + rows + 1
+    payload = torch.empty(max(total, 1), dtype=torch.int32, device=device)
+    pos = 0
+    base = payload.data_ptr()
+    for k in range(C):
+        rows, _, nnz = result.shape(k)
+        result.copy_sparse_to(k, base + 4 * pos, base + 4 * (pos + nnz), base + 4 * (pos + 2 * nnz))
+        pos += 2 * nnz + rows + 1
+    hdr = torch.tensor(header + [total], dtype=torch.int64, device=device)
+    hdrs = [torch.zeros_like(hdr) for _ in range(world)]
+    dist.all_gather(hdrs, hdr, group=group)
+    max_total = max(int(h[-1]) for h in hdrs)
+    if payload.numel() < max_total:
+        padded = torch.zeros(max_total, dtype=torch.int32, device=device)
+        padded[:payload.numel()] = payload
+        payload = padded
+    else:
+        payload = payload[:max_total] if max_total > 0 else payload[:1]
+    bufs = [torch.empty_like(payload) for _ in range(world)] if rank == dst else None
+    dist.gather(payload, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return [h[:-1].cpu().numpy() for h in hdrs], [b[:int(h[-1])] for b, h in zip(bufs, hdrs)]

@@ -188,3 +188,64 @@ def test_row_shards_concatenate(genus):
             off += int(pt[cond][2][-1])
         assert np.array_equal(d, data) and np.array_equal(i, indices)
         assert np.array_equal(np.concatenate(ptr), indptr)
+
+
+def test_int64_failure_modes_match_reference(genus, golden_dir):
+    """int64 mode at large p: the reference raises "Key not found." at p = 20011 and
+    overflow_error at p = 40009 on the level-1062347 genus (tests/golden/errors.json, generated
+    by running the unmodified reference); same exception type and text here."""
+    errors = json.load(open(golden_dir / "errors.json"))
+    g = genus("1062347", False)
+    for key, err in errors.items():
+        p = int(key.split("_")[1][1:])
+        exc = {"invalid_argument": ValueError, "overflow_error": OverflowError}[err["kind"]]
+        with pytest.raises(exc) as info:
+            g.hecke_matrix_sparse(p)
+        assert str(info.value) == err["what"], key
+    # the checked 128-bit mode computes the same primes without error
+    gp = genus("1062347", True)
+    m = gp.hecke_matrix_sparse(20011)
+    data, indices, indptr = m[1]
+    assert (np.add.reduceat(data, indptr[:-1]) == 20012).all()
+
+
+def test_large_prime_digest_and_modes_agree(genus, hecke_digests):
+    """T_10007 on the level-1062347 genus: digest of the reference's int64 output, and the
+    checked 128-bit mode gives the identical matrices (the reference's GMP run is bit-identical
+    to its int64 run)."""
+    key = "L1062347_p10007_z64"
+    if key not in hecke_digests:
+        pytest.skip("slow golden digests not generated")
+    t = genus("1062347", False).table
+    for precise in (False, True):
+        got = genus("1062347", precise).hecke_matrix_sparse(10007)
+        dig = [csr_digest(c, d, *got[int(c)]) for c, d in zip(t.conductors, t.dims)]
+        assert dig == hecke_digests[key], precise
+
+
+def test_size_independent_properties_full_size(genus):
+    """Properties that hold at any size (C5: p = 65521, precise): conductor-1 rows sum to p + 1,
+    columns are strictly ascending with no stored zeros, dense equals sparse on a row block,
+    and T_p is self-adjoint for the automorphism weights: T[n][r] |Aut r| = T[r][n] |Aut n|
+    (the relation the reference's dense path uses to mirror, Genus.h:820-842)."""
+    g = genus("1062347", True)
+    p = 65521
+    csr = g.hecke_matrix_sparse(p)
+    data, indices, indptr = csr[1]
+    assert (np.add.reduceat(data.astype(np.int64), indptr[:-1]) == p + 1).all()
+    assert (data != 0).all()
+    for r in range(0, g.table.N, 97):
+        row = indices[indptr[r]:indptr[r + 1]]
+        assert (np.diff(row) > 0).all()
+    block = g.hecke_matrix_dense(p, 500, 516)[1]
+    for i, r in enumerate(range(500, 516)):
+        want = np.zeros(g.table.N, dtype=np.int32)
+        want[indices[indptr[r]:indptr[r + 1]]] = data[indptr[r]:indptr[r + 1]]
+        assert np.array_equal(block[i], want)
+    from scipy.sparse import csr_matrix
+    N = g.table.N
+    T = csr_matrix((data.astype(np.int64), indices, indptr), shape=(N, N))
+    aut = g.table.num_auts.astype(np.int64)
+    lhs = T.multiply(aut[None, :]).tocsr()          # T[n][r] * aut[r]
+    rhs = T.T.multiply(aut[None, :]).T.tocsr()      # T[r][n] * aut[n] at position (n, r)
+    assert (lhs != rhs).nnz == 0
