@@ -202,8 +202,11 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums, int &
 // holding a run of spins.  For conductor k the row entry of column j is
 //     sum_i chi_k(spin_i) = run - 2 * #{i : popc(spin_i & k) odd}        birch_util.h:81-91
 // kept if lut[k][r] != -1 and the sum is nonzero.                         Genus.h:628-653
-// FILL = false counts the nonzeros per (k, row); FILL = true writes them at
-// indptr offsets (ascending columns, zeros dropped).
+// MODE ROWS_COUNT counts the nonzeros per (k, row); ROWS_FILL writes them at indptr
+// offsets (ascending columns, zeros dropped); ROWS_FUSED does both in one pass: rows are
+// taken in ticket order and each CTA obtains its per-conductor output offset by a
+// decoupled look-back over the rows before it (single-pass chained scan), writing into
+// per-conductor regions sized by an upper bound.
 // ---------------------------------------------------------------------------
 struct RowLaunch {
     int N, K;
@@ -216,12 +219,17 @@ struct RowLaunch {
     const int *rowbase;    // [2^K] offset of conductor k's indptr block in indptr_all
     const int *rowfirst;   // [2^K] lut[k][first included rep >= rep_begin] (row index of the shard's first row)
     int *indptr_all;       // concatenated (rows_k + 1) blocks
-    const i64 *nnzbase;    // [2^K] offset of conductor k in data/indices (FILL)
+    const i64 *nnzbase;    // [2^K] offset of conductor k in data/indices (FILL, FUSED)
+    u64 *lookback;         // [2^K][rows] (flag << 62) | count, zeroed before launch (FUSED)
+    int *ticket;           // row dispenser, zeroed before launch (FUSED)
+    i64 *nnz_out;          // [2^K] written by the last row (FUSED)
     int *data;
     int *indices;
 };
 
-template <bool FILL>
+enum { ROWS_COUNT = 0, ROWS_FILL = 1, ROWS_FUSED = 2 };
+
+template <int MODE>
 __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ RowLaunch L)
 {
     extern __shared__ u32 smem[];
@@ -235,7 +243,16 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
     int *warp_sums = colr + maxcols;
     unsigned short *spins = (unsigned short *)(warp_sums + 256);
 
-    const int lrow = blockIdx.x;
+    __shared__ int s_row;
+    __shared__ i64 s_base[8];
+    if (MODE == ROWS_FUSED)
+    {
+        // tickets are handed out in launch order, so every row a CTA waits on below belongs
+        // to a CTA that is already running or finished: the look-back cannot deadlock
+        if (threadIdx.x == 0) s_row = atomicAdd(L.ticket, 1);
+        __syncthreads();
+    }
+    const int lrow = MODE == ROWS_FUSED ? s_row : (int)blockIdx.x;
     const int n = L.rep_begin + lrow;
     const u32 *Wrow = L.W + (size_t)lrow * L.P1;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -338,7 +355,7 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) cnt[kk] = 0;
 
-        for (int pass = 0; pass < (FILL ? 2 : 1); ++pass)
+        for (int pass = 0; pass < (MODE == ROWS_COUNT ? 1 : 2); ++pass)
         {
             i64 wbase[8];
             if (pass == 1)
@@ -353,8 +370,12 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
                     if (kk < nk && s_npos[kk] != -1)
                     {
                         const int k = kc + kk;
-                        const int out_row = s_npos[kk] - L.rowfirst[k];
-                        wbase[kk] = L.nnzbase[k] + (L.indptr_all + L.rowbase[k])[out_row] + before;
+                        if (MODE == ROWS_FUSED) wbase[kk] = s_base[kk] + before;
+                        else
+                        {
+                            const int out_row = s_npos[kk] - L.rowfirst[k];
+                            wbase[kk] = L.nnzbase[k] + (L.indptr_all + L.rowbase[k])[out_row] + before;
+                        }
                     }
                     cnt[kk] = 0;
                 }
@@ -425,12 +446,42 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
                     for (int kk = 0; kk < 8; ++kk) warp_cnt[kk * 32 + w] = cnt[kk];
                 }
                 __syncthreads();
-                if (!FILL && tid < nk && s_npos[tid] != -1)
+                if (MODE == ROWS_COUNT && tid < nk && s_npos[tid] != -1)
                 {
                     const int k = kc + tid;
                     int total = 0;
                     for (int ww = 0; ww < nw; ++ww) total += warp_cnt[tid * 32 + ww];
                     (L.indptr_all + L.rowbase[k])[s_npos[tid] - L.rowfirst[k] + 1] = total;
+                }
+                if (MODE == ROWS_FUSED)
+                {
+                    if (tid < nk)
+                    {
+                        const int k = kc + tid;
+                        i64 total = 0;
+                        if (s_npos[tid] != -1)
+                            for (int ww = 0; ww < nw; ++ww) total += warp_cnt[tid * 32 + ww];
+                        u64 *state = L.lookback + (size_t)k * L.rows;
+                        const u64 FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VALUE = (1ull << 62) - 1;
+                        if (lrow > 0) atomicExch(state + lrow, FLAG_AGG | (u64)total);
+                        i64 excl = 0;
+                        for (int j = lrow - 1; j >= 0; )
+                        {
+                            const u64 v = *(volatile u64 *)(state + j);
+                            const u64 flag = v >> 62;
+                            if (flag == 0) continue;                 // predecessor still counting
+                            excl += (i64)(v & VALUE);
+                            if (flag == 2) break;                    // inclusive prefix: done
+                            --j;
+                        }
+                        const i64 incl = excl + total;
+                        atomicExch(state + lrow, FLAG_INC | (u64)incl);
+                        s_base[tid] = L.nnzbase[k] + excl;
+                        if (s_npos[tid] != -1)
+                            (L.indptr_all + L.rowbase[k])[s_npos[tid] - L.rowfirst[k] + 1] = (int)incl;
+                        if (lrow == L.rows - 1) L.nnz_out[k] = incl;
+                    }
+                    __syncthreads();
                 }
             }
         }

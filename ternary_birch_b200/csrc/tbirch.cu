@@ -15,6 +15,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -237,6 +238,8 @@ struct tb_genus {
     DevBuf<u64> d_err;
     DevBuf<int> d_tab;          // rowbase | rowfirst | rowcount   (row kernels)
     DevBuf<i64> d_nnz;          // nnz | nnzbase
+    DevBuf<u64> d_lookback;     // [2^K][rows] look-back words + ticket (fused row kernel)
+    bool allow_fused = true;
     u64 *h_err = nullptr;       // pinned [2]
     i64 *h_nnz = nullptr;       // pinned [2 * 2^K]
     int *h_tab = nullptr;       // pinned [3 * 2^K]
@@ -411,6 +414,7 @@ extern "C" int tb_genus_create(const tb_genus_desc *d, tb_genus **out)
     g->q.assign(d->q, d->q + 6 * (size_t)g->N);
     g->lut.assign(d->lut, d->lut + ((size_t)g->N << g->K));
     if (int rc = upload_table(g.get(), d)) return rc;
+    g->allow_fused = getenv("TBIRCH_TWO_PASS_ROWS") == nullptr;   // debugging / A-B switch
     TB_CUDA(g->d_err.reserve(2));
     TB_CUDA(g->d_tab.reserve(3 * (size_t)C));
     TB_CUDA(g->d_nnz.reserve(2 * (size_t)C));
@@ -449,7 +453,7 @@ extern "C" void tb_genus_destroy(tb_genus *g)
     if (!g) return;
     g->d_cur.release(); g->d_rep.release(); g->d_disc.release(); g->d_slots.release(); g->d_lut.release(); g->d_lutT.release();
     g->d_invlut.release(); g->d_base.release(); g->d_W.release(); g->d_rp.release(); g->d_err.release();
-    g->d_tab.release(); g->d_nnz.release();
+    g->d_tab.release(); g->d_nnz.release(); g->d_lookback.release();
     if (g->h_err) cudaFreeHost(g->h_err);
     if (g->h_nnz) cudaFreeHost(g->h_nnz);
     if (g->h_tab) cudaFreeHost(g->h_tab);
@@ -661,9 +665,18 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     for (int k = 0; k < C; ++k) { tab[k] = h->rowbase[k]; tab[C + k] = h->rowfirst[k]; tab[2 * C + k] = h->rows[k]; }
     TB_CUDA(cudaMemcpyAsync(d_tab.ptr, tab, 3 * (size_t)C * sizeof(int), cudaMemcpyHostToDevice, g->stream));
 
-    TB_CUDA(cudaEventRecord(g->ev0, g->stream));
-    if (int rc = launch_neighbors<MODE_PACKED>(g, precise, rb, rows, g->d_W.ptr, nullptr)) { return rc; }
-    TB_CUDA(cudaEventRecord(g->ev1, g->stream));
+    // Single-pass row kernel when the per-conductor output regions, sized by the upper bound
+    // rows_k * min(p+1, dim_k), fit comfortably in HBM; else count / scan / fill.
+    int64_t cap_total = 0;
+    std::vector<int64_t> cap(C);
+    for (int k = 0; k < C; ++k)
+    {
+        cap[k] = (int64_t)h->rows[k] * std::min<int64_t>(P1, g->dims[k]);
+        cap_total += cap[k];
+    }
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const bool fused = g->allow_fused && (size_t)cap_total * 8 <= std::min<size_t>((size_t)48 << 30, total_b / 3);
 
     RowLaunch R;
     memset(&R, 0, sizeof(R));
@@ -672,41 +685,78 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     R.rowbase = d_tab.ptr; R.rowfirst = d_tab.ptr + C;
     R.indptr_all = h->d_indptr.ptr;
     R.nnzbase = d_nnz.ptr + C;
+    R.nnz_out = d_nnz.ptr;
     const size_t smem = rows_smem_bytes(N, P1);
-    if (smem > 227 * 1024)
-    {
+    if (smem > 226 * 1024)
         return fail(TB_ERR_RUNTIME, "libtbirch: row accumulation needs more shared memory than one SM has for this (N, p)");
+    const int threads = (int)std::min<u32>(512, std::max<u32>(64, (P1 + 31) / 32 * 32));
+    static bool attrs_set = false;
+    if (!attrs_set)
+    {
+        const int optin = 226 * 1024;   // 227 KB per CTA minus the kernels' static shared memory
+        TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_COUNT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_FILL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_FUSED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attrs_set = true;
     }
-    int threads = (int)std::min<u32>(512, std::max<u32>(64, (P1 + 31) / 32 * 32));
-    TB_CUDA(cudaFuncSetAttribute(rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TB_CUDA(cudaFuncSetAttribute(rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TB_CUDA(cudaFuncSetAttribute(rows_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    TB_CUDA(cudaFuncSetAttribute(rows_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    rows_kernel<false><<<rows, threads, smem, g->stream>>>(R);
-    ++g_launches;
-    TB_CUDA(cudaGetLastError());
-    indptr_scan_kernel<<<C, 256, 0, g->stream>>>(h->d_indptr.ptr, d_tab.ptr, d_tab.ptr + 2 * C, d_nnz.ptr);
-    ++g_launches;
-    TB_CUDA(cudaGetLastError());
 
-    TB_CUDA(cudaMemcpyAsync(g->h_err, g->d_err.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, g->stream));
-    TB_CUDA(cudaMemcpyAsync(g->h_nnz, d_nnz.ptr, C * sizeof(i64), cudaMemcpyDeviceToHost, g->stream));
-    TB_CUDA(cudaStreamSynchronize(g->stream));
-    if (int rc = check_errors(g)) { return rc; }
-    for (int k = 0; k < C; ++k) h->nnz[k] = g->h_nnz[k];
+    TB_CUDA(cudaEventRecord(g->ev0, g->stream));
+    if (int rc = launch_neighbors<MODE_PACKED>(g, precise, rb, rows, g->d_W.ptr, nullptr)) { return rc; }
+    TB_CUDA(cudaEventRecord(g->ev1, g->stream));
 
-    int64_t total_nnz = 0;
-    for (int k = 0; k < C; ++k) { h->nnzbase[k] = total_nnz; total_nnz += h->nnz[k]; }
-    TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(total_nnz, 1), g->stream));
-    TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(total_nnz, 1), g->stream));
-    for (int k = 0; k < C; ++k) g->h_nnz[C + k] = h->nnzbase[k];
-    TB_CUDA(cudaMemcpyAsync(d_nnz.ptr + C, g->h_nnz + C, C * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
-    R.data = h->d_data.ptr; R.indices = h->d_indices.ptr;
-    rows_kernel<true><<<rows, threads, smem, g->stream>>>(R);
-    ++g_launches;
-    TB_CUDA(cudaGetLastError());
-    TB_CUDA(cudaEventRecord(g->ev2, g->stream));
-    TB_CUDA(cudaStreamSynchronize(g->stream));
+    if (fused)
+    {
+        int64_t off = 0;
+        for (int k = 0; k < C; ++k) { h->nnzbase[k] = off; g->h_nnz[C + k] = off; off += cap[k]; }
+        TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(cap_total, 1), g->stream));
+        TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(cap_total, 1), g->stream));
+        TB_CUDA(g->d_lookback.reserve((size_t)C * rows + 2));
+        TB_CUDA(cudaMemsetAsync(g->d_lookback.ptr, 0, ((size_t)C * rows + 2) * sizeof(u64), g->stream));
+        TB_CUDA(cudaMemcpyAsync(d_nnz.ptr + C, g->h_nnz + C, C * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
+        R.lookback = g->d_lookback.ptr;
+        R.ticket = (int *)(g->d_lookback.ptr + (size_t)C * rows);
+        R.data = h->d_data.ptr; R.indices = h->d_indices.ptr;
+        rows_kernel<ROWS_FUSED><<<rows, threads, smem, g->stream>>>(R);
+        ++g_launches;
+        TB_CUDA(cudaGetLastError());
+        TB_CUDA(cudaEventRecord(g->ev2, g->stream));
+        TB_CUDA(cudaMemcpyAsync(g->h_err, g->d_err.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, g->stream));
+        TB_CUDA(cudaMemcpyAsync(g->h_nnz, d_nnz.ptr, C * sizeof(i64), cudaMemcpyDeviceToHost, g->stream));
+        TB_CUDA(cudaStreamSynchronize(g->stream));
+        if (int rc = check_errors(g)) { return rc; }
+        for (int k = 0; k < C; ++k) h->nnz[k] = g->h_nnz[k];
+    }
+    else
+    {
+        rows_kernel<ROWS_COUNT><<<rows, threads, smem, g->stream>>>(R);
+        ++g_launches;
+        TB_CUDA(cudaGetLastError());
+        indptr_scan_kernel<<<C, 256, 0, g->stream>>>(h->d_indptr.ptr, d_tab.ptr, d_tab.ptr + 2 * C, d_nnz.ptr);
+        ++g_launches;
+        TB_CUDA(cudaGetLastError());
+
+        TB_CUDA(cudaMemcpyAsync(g->h_err, g->d_err.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, g->stream));
+        TB_CUDA(cudaMemcpyAsync(g->h_nnz, d_nnz.ptr, C * sizeof(i64), cudaMemcpyDeviceToHost, g->stream));
+        TB_CUDA(cudaStreamSynchronize(g->stream));
+        if (int rc = check_errors(g)) { return rc; }
+        for (int k = 0; k < C; ++k) h->nnz[k] = g->h_nnz[k];
+
+        int64_t total_nnz = 0;
+        for (int k = 0; k < C; ++k) { h->nnzbase[k] = total_nnz; total_nnz += h->nnz[k]; }
+        TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(total_nnz, 1), g->stream));
+        TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(total_nnz, 1), g->stream));
+        for (int k = 0; k < C; ++k) g->h_nnz[C + k] = h->nnzbase[k];
+        TB_CUDA(cudaMemcpyAsync(d_nnz.ptr + C, g->h_nnz + C, C * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
+        R.data = h->d_data.ptr; R.indices = h->d_indices.ptr;
+        rows_kernel<ROWS_FILL><<<rows, threads, smem, g->stream>>>(R);
+        ++g_launches;
+        TB_CUDA(cudaGetLastError());
+        TB_CUDA(cudaEventRecord(g->ev2, g->stream));
+        TB_CUDA(cudaStreamSynchronize(g->stream));
+    }
     cudaEventElapsedTime(&g->last_ms_nbr, g->ev0, g->ev1);
     cudaEventElapsedTime(&g->last_ms_rows, g->ev1, g->ev2);
     g->last_neighbors = (int64_t)rows * P1;

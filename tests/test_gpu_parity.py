@@ -251,6 +251,5 @@ def test_size_independent_properties_full_size(genus):
     N = g.table.N
     T = csr_matrix((data.astype(np.int64), indices, indptr), shape=(N, N))
     aut = g.table.num_auts.astype(np.int64)
-    lhs = T.multiply(aut[None, :]).tocsr()          # T[n][r] * aut[r]
-    rhs = T.T.multiply(aut[None, :]).T.tocsr()      # T[r][n] * aut[n] at position (n, r)
-    assert (lhs != rhs).nnz == 0
+    TA = T.multiply(aut[None, :]).tocsr()           # (T A)[n][r] = T[n][r] * aut[r]
+    assert (TA != TA.T.tocsr()).nnz == 0            # T A is symmetric
