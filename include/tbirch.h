@@ -143,6 +143,30 @@ void tb_isoseq_close(tb_isoseq *it);
 int tb_neighbor_records(tb_genus *g, uint64_t p, int precise, int64_t rep_begin, int64_t rep_end,
                         int64_t *records);
 
+/* ---- genus construction (the caller side of the hot path) -- */
+typedef struct tb_prime_symbol {   /* PrimeSymbol<R>, birch.h:107-112 */
+    int64_t p;
+    int32_t power;
+    int32_t ramified;
+} tb_prime_symbol;
+
+typedef struct tb_table tb_table;
+
+/* QuadForm<Z>::get_quad_form (QuadForm.cpp:444-777): the positive definite ternary form
+ * (a,b,c,f,g,h) with the given discriminant prod p^power and ramification. */
+int tb_quad_form(const tb_prime_symbol *symbols, int64_t count, int64_t form[6]);
+/* Genus<R>::Genus(q, symbols, seed) (Genus.h:37-246): enumerate the genus of `form` by
+ * p-neighbor walking in the reference's discovery order (seed = 0 draws a random seed, as
+ * the reference does), compose the isometries to the mother form (189-217) and derive
+ * dims / lut_positions from the automorphisms' spinor norms (219-244). */
+int tb_genus_enumerate(const int64_t form[6], const tb_prime_symbol *symbols, int64_t count,
+                       uint64_t seed, tb_table **out);
+/* Fill `desc` with pointers into the table (valid until tb_table_destroy); the extra arrays
+ * are GenusRep::parent, GenusRep::p and QuadForm::num_automorphisms per representative. */
+int tb_table_desc(const tb_table *t, tb_genus_desc *desc, const int64_t **parent,
+                  const int64_t **rep_prime, const int64_t **num_auts);
+void tb_table_destroy(tb_table *t);
+
 /* ---- integer-pipe microbenchmark -------------------------------------- */
 /* Measures the int32 issue peak used as the roofline denominator: runs an
  * unrolled IMAD + IADD3/LOP3 chain on every SM.  Returns int32 op/s. */

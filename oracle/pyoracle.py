@@ -156,7 +156,7 @@ class RefBinary:
     def _stream(self, commands_before_out):
         with tempfile.TemporaryDirectory() as d:
             out = os.path.join(d, "out.bin")
-            self._run(list(commands_before_out) + [out])
+            self._run(list(commands_before_out) + [out], timeout=900)
             return np.fromfile(out, dtype=np.int64)
 
     def genus(self) -> GenusArrays:

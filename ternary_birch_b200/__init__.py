@@ -8,9 +8,10 @@ The compute lives in ``libtbirch.so`` (hand-written CUDA, C ABI in
 (``genus``).  There is no CPU fallback: importing works anywhere, computing
 needs the CUDA library and a GPU.
 """
-from .table import GenusTable, load_genus_table, save_genus_table  # noqa: F401
+from .table import (GenusTable, build_genus_table, load_genus_table, prime_symbols, quad_form,  # noqa: F401
+                    save_genus_table)
 from .genus import Genus, IsometrySequence, BirchGenus, EigenvectorManager  # noqa: F401
 from . import cabi  # noqa: F401
 
-__all__ = ["GenusTable", "load_genus_table", "save_genus_table", "Genus", "IsometrySequence",
+__all__ = ["GenusTable", "build_genus_table", "quad_form", "prime_symbols", "load_genus_table", "save_genus_table", "Genus", "IsometrySequence",
            "BirchGenus", "EigenvectorManager", "cabi"]

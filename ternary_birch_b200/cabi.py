@@ -26,6 +26,10 @@ class GenusDesc(ctypes.Structure):
                 ("sinv", ctypes.c_void_p), ("scalar", ctypes.c_void_p), ("lut", ctypes.c_void_p)]
 
 
+class PrimeSymbol(ctypes.Structure):
+    _fields_ = [("p", ctypes.c_int64), ("power", ctypes.c_int32), ("ramified", ctypes.c_int32)]
+
+
 def lib() -> ctypes.CDLL:
     """Load libtbirch.so; fail loudly when the CUDA extension has not been built."""
     global _lib
@@ -71,6 +75,11 @@ def lib() -> ctypes.CDLL:
     L.tb_isoseq_close.restype = None
     L.tb_neighbor_records.argtypes = [vp, u64, i32, i64, i64, vp]
     L.tb_int_peak.argtypes = [vp, vp, vp]
+    L.tb_quad_form.argtypes = [ctypes.POINTER(PrimeSymbol), i64, vp]
+    L.tb_genus_enumerate.argtypes = [vp, ctypes.POINTER(PrimeSymbol), i64, u64, ctypes.POINTER(vp)]
+    L.tb_table_desc.argtypes = [vp, ctypes.POINTER(GenusDesc), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    L.tb_table_destroy.argtypes = [vp]
+    L.tb_table_destroy.restype = None
     if L.tb_abi_version() != 1:
         raise RuntimeError("libtbirch.so ABI version mismatch")
     _lib = L
@@ -85,6 +94,7 @@ EXPORTS = [
     "tb_hecke_dim", "tb_hecke_rows", "tb_hecke_row_begin", "tb_hecke_nnz", "tb_hecke_copy_sparse",
     "tb_hecke_copy_dense", "tb_hecke_destroy", "tb_eigenvalues", "tb_isoseq_open", "tb_isoseq_done",
     "tb_isoseq_next", "tb_isoseq_read", "tb_isoseq_close", "tb_neighbor_records", "tb_int_peak",
+    "tb_quad_form", "tb_genus_enumerate", "tb_table_desc", "tb_table_destroy",
 ]
 
 

@@ -10,6 +10,7 @@
 // There is no CPU fallback: without a CUDA device every compute call fails.
 #include "../../include/tbirch.h"
 #include "tb_kernels.cuh"
+#include "tb_build.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -1002,6 +1003,253 @@ extern "C" int tb_isoseq_next(tb_isoseq *it, int64_t isometry[9], int64_t *denom
 }
 
 extern "C" void tb_isoseq_close(tb_isoseq *it) { delete it; }
+
+// ---------------------------------------------------------------------------
+// genus construction
+// ---------------------------------------------------------------------------
+struct tb_table {
+    BuiltGenus g;
+};
+
+static std::vector<PrimeSym> to_symbols(const tb_prime_symbol *symbols, int64_t count)
+{
+    std::vector<PrimeSym> out;
+    for (int64_t i = 0; i < count; ++i) out.push_back(PrimeSym{symbols[i].p, (int)symbols[i].power, symbols[i].ramified != 0});
+    return out;
+}
+
+extern "C" int tb_quad_form(const tb_prime_symbol *symbols, int64_t count, int64_t form[6])
+{
+    if (!symbols || !form || count <= 0) return fail(TB_ERR_INVALID_ARGUMENT, "tb_quad_form: bad argument");
+    if (int rc = require_device()) return rc;
+    try { quad_form_for(to_symbols(symbols, count), 0, form); }
+    catch (const std::invalid_argument &e) { return fail(TB_ERR_INVALID_ARGUMENT, e.what()); }
+    catch (const std::exception &e) { return fail(TB_ERR_RUNTIME, e.what()); }
+    return TB_OK;
+}
+
+static void make_prime_ctx(uint64_t p, double lambda_min, const u32 *inv_lut, PrimeCtx &pc)
+{
+    memset(&pc, 0, sizeof(pc));
+    pc.p = (u32)p;
+    pc.pp = p * p;
+    pc.dp = make_invdiv(p);
+    pc.dpp = make_invdiv(p * p);
+    pc.use_lut = (p > 2 && p < (1ull << 22)) ? 1u : 0u;
+    pc.m32 = (p > 2 && p < (1ull << 16)) ? (u32)((1ull << 32) / p) : 0u;
+    pc.fp64_reduce = (lambda_min > 0 && (double)p * sqrt(1125899906842624.0 / lambda_min) < 4503599627370496.0) ? 1u : 0u;
+    pc.inv_lut = inv_lut;
+}
+
+// Genus<R>::Genus, Genus.h:37-246.
+static int enumerate_genus(const int64_t form[6], const std::vector<PrimeSym> &symbols, uint64_t seed, BuiltGenus &G)
+{
+    if (symbols.size() > 63) return fail(TB_ERR_DOMAIN, "Must have 63 or fewer prime divisors.");
+    if (symbols.size() > TB_MAX_PRIMES) return fail(TB_ERR_RUNTIME, "libtbirch: more than 16 prime divisors");
+    if (seed == 0) { std::random_device rd; seed = rd(); }   // Genus.h:39-43
+    const big a0 = form[0], b0 = form[1], c0 = form[2], f0 = form[3], g0 = form[4], h0 = form[5];
+    const big disc = a0 * (4 * b0 * c0 - f0 * f0) - b0 * g0 * g0 + h0 * (f0 * g0 - c0 * h0);
+    if (disc <= 0 || disc != (big)(int64_t)disc) return fail(TB_ERR_INVALID_ARGUMENT, "tb_genus_enumerate: discriminant out of range");
+    G.K = (int64_t)symbols.size();
+    G.seed = seed;
+    G.disc = (int64_t)disc;
+    for (const PrimeSym &s : symbols) G.primes.push_back(s.p);
+    const int64_t C = 1ll << G.K;
+    G.conductors.assign(1, 1);                               // Genus.h:62-78
+    {
+        size_t bits = 0, mask = 1;
+        for (int64_t n = 1; n < C; ++n)
+        {
+            if ((size_t)n == 2 * mask) { ++bits; mask = (size_t)1 << bits; }
+            G.conductors.push_back(G.primes[bits] * G.conductors[n ^ mask]);
+        }
+    }
+    const big mass_x24 = genus_mass_x24(form, disc, symbols);
+
+    std::vector<std::array<int64_t, 6>> q;                   // representatives in discovery order
+    std::vector<std::array<big, 9>> s;                       // parent -> child isometries
+    std::vector<int64_t> parent, rp;
+    std::unordered_map<FormKey, int, FormKeyHash> index;
+    auto add_rep = [&](const i64 *f, const i64 *iso, int64_t par, int64_t prime) {
+        FormKey key;
+        memcpy(key.v, f, sizeof(key.v));
+        if (!index.emplace(key, (int)q.size()).second) return false;
+        q.push_back({(int64_t)f[0], (int64_t)f[1], (int64_t)f[2], (int64_t)f[3], (int64_t)f[4], (int64_t)f[5]});
+        std::array<big, 9> m;
+        for (int i = 0; i < 9; ++i) m[i] = iso ? (big)iso[i] : (big)((i % 4) == 0);
+        s.push_back(m);
+        parent.push_back(par);
+        rp.push_back(prime);
+        return true;
+    };
+    auto auts_of = [&](const i64 *f) { return (int64_t)(2 * (proper_automorphisms((const int64_t *)f).size() + 1)); };
+    add_rep((const i64 *)form, nullptr, -1, 1);
+    big sum_x24 = 48 / auts_of((const i64 *)form);
+    bool done = (sum_x24 == mass_x24);
+
+    cudaStream_t st = 0;
+    DevBuf<i64> d_forms, d_rec;
+    DevBuf<u32> d_base, d_lut;
+    DevBuf<RepPrime> d_rp;
+    auto release = [&]() { d_forms.release(); d_rec.release(); d_base.release(); d_lut.release(); d_rp.release(); };
+    int64_t p = 1;
+    while (!done)
+    {
+        do { p = next_prime64(p); } while (disc % p == 0);   // Genus.h:116-123
+        if (p >= 65536) { release(); return fail(TB_ERR_RUNTIME, "tb_genus_enumerate: mass not reached below p = 2^16 (inconsistent input?)"); }
+        PrimeCtx pc;
+        if (p > 2)
+        {
+            if (d_lut.reserve((size_t)p) != cudaSuccess) { release(); return fail(TB_ERR_RUNTIME, "CUDA allocation failed"); }
+        }
+        make_prime_ctx((uint64_t)p, 0.0, d_lut.ptr, pc);
+        if (pc.use_lut)
+        {
+            inverse_lut_kernel<<<(unsigned)((p + 255) / 256), 256, 0, st>>>(pc, d_lut.ptr);
+            ++g_launches;
+        }
+        HostFp F((uint64_t)p, seed);                         // one Fp (one RNG stream) per prime
+        size_t current = 0;
+        while (!done && current < q.size())
+        {
+            // one wave: every representative not yet expanded at this prime
+            const size_t wave_begin = current, wave_end = q.size();
+            const int rows = (int)(wave_end - wave_begin);
+            const u32 P1 = (u32)p + 1;
+            std::vector<i64> forms((size_t)rows * TB_REC_WORDS, 0);
+            std::vector<u32> base(3 * (size_t)rows);
+            for (int i = 0; i < rows; ++i)
+            {
+                memcpy(&forms[(size_t)i * TB_REC_WORDS], q[wave_begin + i].data(), 6 * sizeof(i64));
+                base_point(F, (const int64_t *)q[wave_begin + i].data(), &base[3 * (size_t)i]);
+            }
+            const size_t nrec = (size_t)rows * P1;
+            if (d_forms.reserve(forms.size()) != cudaSuccess || d_base.reserve(base.size()) != cudaSuccess ||
+                d_rp.reserve(rows) != cudaSuccess || d_rec.reserve(nrec * 16) != cudaSuccess)
+            { release(); return fail(TB_ERR_RUNTIME, "CUDA allocation failed"); }
+            cudaMemcpyAsync(d_forms.ptr, forms.data(), forms.size() * sizeof(i64), cudaMemcpyHostToDevice, st);
+            cudaMemcpyAsync(d_base.ptr, base.data(), base.size() * sizeof(u32), cudaMemcpyHostToDevice, st);
+            GenusCtx gc;
+            memset(&gc, 0, sizeof(gc));
+            gc.N = rows; gc.K = 0; gc.cur = d_forms.ptr; gc.rep = d_forms.ptr;
+            prep_reps_kernel<<<(rows + 127) / 128, 128, 0, st>>>(gc, pc, d_base.ptr, 0, rows, d_rp.ptr);
+            EnumLaunch L;
+            memset(&L, 0, sizeof(L));
+            L.rows = rows; L.P1 = P1; L.total = nrec; L.dP1 = make_invdiv(P1); L.rp = d_rp.ptr; L.records = d_rec.ptr;
+            enum_kernel<<<(unsigned)((nrec + TB_NBR_THREADS - 1) / TB_NBR_THREADS), TB_NBR_THREADS, 0, st>>>(gc, pc, L);
+            g_launches += 2;
+            std::vector<i64> rec(nrec * 16);
+            cudaMemcpyAsync(rec.data(), d_rec.ptr, rec.size() * sizeof(i64), cudaMemcpyDeviceToHost, st);
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { release(); return fail(TB_ERR_RUNTIME, std::string("CUDA error: ") + cudaGetErrorString(e)); }
+
+            for (int i = 0; i < rows && !done; ++i)          // Genus.h:128-175, in order
+            {
+                for (u32 t = 0; t < P1 && !done; ++t)
+                {
+                    const i64 *r = &rec[((size_t)i * P1 + t) * 16];
+                    if (r[15] != 0) { release(); return fail(TB_ERR_OVERFLOW, MSG_OVERFLOW); }
+                    if (add_rep(r, r + 6, (int64_t)(wave_begin + i), p))
+                    {
+                        sum_x24 += 48 / auts_of(r);
+                        done = (sum_x24 == mass_x24);
+                    }
+                }
+                ++current;
+            }
+            if (sum_x24 > mass_x24) { release(); return fail(TB_ERR_RUNTIME, "tb_genus_enumerate: mass exceeded (inconsistent form / symbols)"); }
+        }
+    }
+    release();
+
+    // isometries to / from the mother form, spinor-prime exponents     Genus.h:189-217
+    const size_t N = q.size();
+    std::vector<std::array<big, 9>> S(N), Sinv(N);
+    std::vector<big> scalar(N, 1);
+    G.N = (int64_t)N;
+    G.dims.assign(C, 0);
+    G.lut.assign((size_t)C * N, -1);
+    for (size_t n = 0; n < N; ++n)
+    {
+        if (n == 0)
+        {
+            for (int i = 0; i < 9; ++i) S[0][i] = Sinv[0][i] = (i % 4) == 0;
+        }
+        else
+        {
+            const std::array<big, 9> &m = s[n];
+            const big pr = rp[n];
+            std::array<big, 9> adj;                          // Isometry::inverse(p), Isometry.h:33-46
+            adj[0] = (m[4] * m[8] - m[5] * m[7]) / pr; adj[1] = (m[2] * m[7] - m[1] * m[8]) / pr; adj[2] = (m[1] * m[5] - m[2] * m[4]) / pr;
+            adj[3] = (m[5] * m[6] - m[3] * m[8]) / pr; adj[4] = (m[0] * m[8] - m[2] * m[6]) / pr; adj[5] = (m[2] * m[3] - m[0] * m[5]) / pr;
+            adj[6] = (m[3] * m[7] - m[4] * m[6]) / pr; adj[7] = (m[1] * m[6] - m[0] * m[7]) / pr; adj[8] = (m[0] * m[4] - m[1] * m[3]) / pr;
+            const size_t par = (size_t)parent[n];
+            mat3_mul(adj.data(), Sinv[par].data(), Sinv[n].data());
+            mat3_mul(S[par].data(), m.data(), S[n].data());
+            scalar[n] = scalar[par] * pr;
+        }
+        // which conductors see this representative                     Genus.h:219-244
+        const std::vector<SmallIso> auts = proper_automorphisms(q[n].data());
+        std::vector<char> ignore(C, 0);
+        for (const SmallIso &au : auts)
+        {
+            const u64 vals = host_spinor_norm(q[n].data(), au, G.primes);
+            for (int64_t k = 0; k < C; ++k)
+                if (!ignore[k] && (__builtin_popcountll(vals & (u64)k) & 1)) ignore[k] = 1;
+        }
+        G.num_auts.push_back((int64_t)(2 * (auts.size() + 1)));
+        for (int64_t k = 0; k < C; ++k)
+            if (!ignore[k]) G.lut[(size_t)k * N + n] = (int32_t)G.dims[k]++;
+    }
+    for (size_t n = 0; n < N; ++n)
+    {
+        for (int i = 0; i < 6; ++i) G.q.push_back(q[n][i]);
+        for (int i = 0; i < 9; ++i)
+        {
+            if (S[n][i] != (big)(int64_t)S[n][i] || Sinv[n][i] != (big)(int64_t)Sinv[n][i])
+                return fail(TB_ERR_OVERFLOW, "tb_genus_enumerate: composed isometry exceeds 64 bits");
+            G.s.push_back((int64_t)S[n][i]);
+        }
+        for (int i = 0; i < 9; ++i) G.sinv.push_back((int64_t)Sinv[n][i]);
+        if (scalar[n] != (big)(int64_t)scalar[n]) return fail(TB_ERR_OVERFLOW, "tb_genus_enumerate: scalar exceeds 64 bits");
+        G.scalar.push_back((int64_t)scalar[n]);
+        G.parent.push_back(parent[n]);
+        G.p.push_back(rp[n]);
+    }
+    return TB_OK;
+}
+
+extern "C" int tb_genus_enumerate(const int64_t form[6], const tb_prime_symbol *symbols, int64_t count,
+                                  uint64_t seed, tb_table **out)
+{
+    if (!form || !symbols || !out || count <= 0) return fail(TB_ERR_INVALID_ARGUMENT, "tb_genus_enumerate: bad argument");
+    *out = nullptr;
+    if (int rc = require_device()) return rc;
+    std::unique_ptr<tb_table> t(new tb_table);
+    try
+    {
+        if (int rc = enumerate_genus(form, to_symbols(symbols, count), seed, t->g)) return rc;
+    }
+    catch (const std::exception &e) { return fail(TB_ERR_RUNTIME, e.what()); }
+    *out = t.release();
+    return TB_OK;
+}
+
+extern "C" int tb_table_desc(const tb_table *t, tb_genus_desc *d, const int64_t **parent, const int64_t **rep_prime,
+                             const int64_t **num_auts)
+{
+    if (!t || !d) return fail(TB_ERR_INVALID_ARGUMENT, "tb_table_desc: null argument");
+    const BuiltGenus &g = t->g;
+    d->N = g.N; d->K = g.K; d->seed = g.seed; d->disc = g.disc;
+    d->primes = g.primes.data(); d->conductors = g.conductors.data(); d->dims = g.dims.data();
+    d->q = g.q.data(); d->s = g.s.data(); d->sinv = g.sinv.data(); d->scalar = g.scalar.data(); d->lut = g.lut.data();
+    if (parent) *parent = g.parent.data();
+    if (rep_prime) *rep_prime = g.p.data();
+    if (num_auts) *num_auts = g.num_auts.data();
+    return TB_OK;
+}
+
+extern "C" void tb_table_destroy(tb_table *t) { delete t; }
 
 // ---------------------------------------------------------------------------
 // integer-pipe microbenchmark

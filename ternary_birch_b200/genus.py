@@ -19,7 +19,7 @@ from math import exp, lgamma, log
 import numpy as np
 
 from . import cabi
-from .table import GenusTable, load_genus_table
+from .table import GenusTable, build_genus_table, load_genus_table, prime_symbols
 
 
 def _ptr(a: np.ndarray) -> ctypes.c_void_p:
@@ -365,9 +365,17 @@ class BirchGenus:
     is importable (as the pyx returns), else ``(data, indices, indptr)``.
     """
 
-    def __init__(self, table):
-        if not isinstance(table, GenusTable):
-            table = load_genus_table(table)
+    def __init__(self, level, ramified_primes=None, seed=None):
+        """``BirchGenus(level, ramified_primes=None, seed=None)`` as in the pyx (139-205): builds the
+        quadratic form and enumerates the genus on the GPU.  A ``GenusTable`` (or a path to one)
+        may be passed instead of the level to reuse an existing table."""
+        if isinstance(level, GenusTable):
+            table = level
+        elif isinstance(level, (str, bytes)) or hasattr(level, "__fspath__"):
+            table = load_genus_table(level)
+        else:
+            table = build_genus_table(int(level), ramified_primes, seed)
+            self.ramified_primes_ = prime_symbols(int(level), ramified_primes)[1]
         self.table = table
         self.level_ = table.level
         self.dims = {int(c): int(d) for c, d in zip(table.conductors, table.dims)}

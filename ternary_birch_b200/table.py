@@ -94,3 +94,71 @@ def save_genus_table(table: GenusTable, path) -> None:
         np.savez_compressed(path, stream=table.to_stream())
     else:
         table.to_stream().tofile(path)
+
+
+def _factor(n: int):
+    out, d = [], 2
+    while d * d <= n:
+        e = 0
+        while n % d == 0:
+            n //= d
+            e += 1
+        if e:
+            out.append((d, e))
+        d += 1
+    if n > 1:
+        out.append((n, 1))
+    return out
+
+
+def prime_symbols(level: int, ramified_primes=None):
+    """The (p, power, ramified) triples BirchGenus.__init__ builds (ternary_birch.pyx:146-167):
+    without an explicit list, every prime is ramified when their number is odd, all but the
+    largest otherwise."""
+    facs = _factor(int(level))
+    ps = [p for p, _ in facs]
+    if ramified_primes is None:
+        ram = ps[:-1] if len(ps) % 2 == 0 else ps[:]
+    else:
+        ram = [p for p in ramified_primes if p in ps]
+    return [(p, e, p in ram) for p, e in facs], ram
+
+
+def quad_form(symbols):
+    """QuadForm<Z>::get_quad_form (QuadForm.cpp:444-777) through the C ABI."""
+    import ctypes
+    from . import cabi
+    arr = (cabi.PrimeSymbol * len(symbols))(*[cabi.PrimeSymbol(int(p), int(e), int(bool(r))) for p, e, r in symbols])
+    form = np.zeros(6, dtype=np.int64)
+    cabi.check(cabi.lib().tb_quad_form(arr, len(symbols), ctypes.c_void_p(form.ctypes.data)))
+    return [int(x) for x in form]
+
+
+def build_genus_table(level: int, ramified_primes=None, seed=None, form=None) -> GenusTable:
+    """Genus<Z>(q, symbols, seed) (Genus.h:37-246) through the C ABI: enumerate the genus of
+    the given level on the GPU, in the reference's discovery order."""
+    import ctypes
+    from . import cabi
+    symbols, _ = prime_symbols(level, ramified_primes)
+    L = cabi.lib()
+    arr = (cabi.PrimeSymbol * len(symbols))(*[cabi.PrimeSymbol(int(p), int(e), int(bool(r))) for p, e, r in symbols])
+    q = np.asarray(form if form is not None else quad_form(symbols), dtype=np.int64)
+    handle = ctypes.c_void_p()
+    cabi.check(L.tb_genus_enumerate(ctypes.c_void_p(q.ctypes.data), arr, len(symbols), int(seed or 0), ctypes.byref(handle)))
+    try:
+        d = cabi.GenusDesc()
+        parent, rep_p, auts = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        cabi.check(L.tb_table_desc(handle, ctypes.byref(d), ctypes.byref(parent), ctypes.byref(rep_p), ctypes.byref(auts)))
+        N, K = int(d.N), int(d.K)
+        C = 1 << K
+
+        def arr64(ptr, n):
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_int64)), shape=(n,)).copy()
+
+        lut = np.ctypeslib.as_array(ctypes.cast(d.lut, ctypes.POINTER(ctypes.c_int32)), shape=(C * N,)).copy()
+        return GenusTable(N, K, int(d.seed), int(d.disc), arr64(d.primes, K), arr64(d.conductors, C), arr64(d.dims, C),
+                          arr64(d.q, 6 * N).reshape(N, 6), arr64(d.s, 9 * N).reshape(N, 9),
+                          arr64(d.sinv, 9 * N).reshape(N, 9), arr64(d.scalar, N), arr64(parent, N), arr64(rep_p, N),
+                          arr64(auts, N), lut.reshape(C, N))
+    finally:
+        L.tb_table_destroy(handle)
