@@ -20,12 +20,25 @@ class Genus
 public:
     Genus() = default;
 
-    // The reference enumerates the genus here (Genus.h:37-246).  Enumeration is the "next"
-    // row of this project's scope; until then a Genus is made from a table.
-    Genus(const QuadForm<R>&, const std::vector<PrimeSymbol<R>>&, W64 = 0)
+    // Genus<R>::Genus (Genus.h:37-246): enumerate the genus of q in the reference's discovery
+    // order -- tb_genus_enumerate in the library (seed = 0 draws a random seed).
+    Genus(const QuadForm<R>& q, const std::vector<PrimeSymbol<R>>& symbols, W64 seed = 0)
     {
-        throw std::logic_error("Genus enumeration is outside the accelerated p-neighbor path; "
-                               "construct from a genus table (Genus::from_table).");
+        std::vector<tb_prime_symbol> syms;
+        for (const PrimeSymbol<R>& s : symbols)
+        {
+            tb_prime_symbol t;
+            t.p = Traits::to_i64(s.p); t.power = s.power; t.ramified = s.ramified ? 1 : 0;
+            syms.push_back(t);
+        }
+        const int64_t form[6] = { Traits::to_i64(q.a()), Traits::to_i64(q.b()), Traits::to_i64(q.c()),
+                                  Traits::to_i64(q.f()), Traits::to_i64(q.g()), Traits::to_i64(q.h()) };
+        tb_table *built = nullptr;
+        tbirch::check(tb_genus_enumerate(form, syms.data(), (int64_t)syms.size(), seed, &built));
+        tb_genus_desc d;
+        tbirch::check(tb_table_desc(built, &d, nullptr, nullptr, nullptr));
+        table_ = tbirch::Table::from_desc(d);
+        tb_table_destroy(built);
     }
 
     static Genus<R> from_table(std::shared_ptr<tbirch::Table> table)

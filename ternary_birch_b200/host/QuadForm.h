@@ -29,13 +29,22 @@ public:
         return a_ == q.a_ && b_ == q.b_ && c_ == q.c_ && f_ == q.f_ && g_ == q.g_ && h_ == q.h_;
     }
 
-    // QuadForm.cpp:444-777 builds the form of a given ramification by a search that is
-    // not on the accelerated path (one call per genus, milliseconds).  A deployment keeps
-    // the reference's own translation unit for it; this facade does not re-implement it.
-    static QuadForm<R> get_quad_form(const std::vector<PrimeSymbol<R>>&)
+    // QuadForm<Z>::get_quad_form (QuadForm.cpp:444-777): the positive definite ternary form of
+    // discriminant prod p^power ramified at the flagged primes -- tb_quad_form in the library.
+    static QuadForm<R> get_quad_form(const std::vector<PrimeSymbol<R>>& primes)
     {
-        throw std::logic_error("QuadForm::get_quad_form is outside the accelerated p-neighbor path; "
-                               "link the reference's QuadForm.cpp or build the genus from a table.");
+        typedef tbirch::IntegerTraits<R> Traits;
+        std::vector<tb_prime_symbol> symbols;
+        for (const PrimeSymbol<R>& s : primes)
+        {
+            tb_prime_symbol t;
+            t.p = Traits::to_i64(s.p); t.power = s.power; t.ramified = s.ramified ? 1 : 0;
+            symbols.push_back(t);
+        }
+        int64_t f[6];
+        tbirch::check(tb_quad_form(symbols.data(), (int64_t)symbols.size(), f));
+        return QuadForm<R>(Traits::from_i64(f[0]), Traits::from_i64(f[1]), Traits::from_i64(f[2]),
+                           Traits::from_i64(f[3]), Traits::from_i64(f[4]), Traits::from_i64(f[5]));
     }
 
 protected:

@@ -103,6 +103,21 @@ struct Table {
         if (!dev) { tb_genus_desc d = desc(); check(tb_genus_create(&d, &dev)); }
         return dev;
     }
+    static std::shared_ptr<Table> from_desc(const tb_genus_desc& d)
+    {
+        std::shared_ptr<Table> t = std::make_shared<Table>();
+        t->N = d.N; t->K = d.K; t->seed = d.seed; t->disc = d.disc;
+        const size_t N = (size_t)d.N, C = (size_t)1 << d.K;
+        t->primes.assign(d.primes, d.primes + d.K);
+        t->conductors.assign(d.conductors, d.conductors + C);
+        t->dims.assign(d.dims, d.dims + C);
+        t->q.assign(d.q, d.q + 6 * N);
+        t->s.assign(d.s, d.s + 9 * N);
+        t->sinv.assign(d.sinv, d.sinv + 9 * N);
+        t->scalar.assign(d.scalar, d.scalar + N);
+        t->lut.assign(d.lut, d.lut + C * N);
+        return t;
+    }
     // flat int64 stream, layout of ternary_birch_b200/table.py ("TBGENUS1")
     static std::shared_ptr<Table> from_stream(const int64_t *a, size_t len)
     {

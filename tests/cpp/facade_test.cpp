@@ -94,6 +94,14 @@ int main(int argc, char **argv)
         Genus<Big> gz = Genus<Big>::from_table(table);
         Genus<int64_t> g64(gz);
         out.push_back((int64_t)g64.size());
+        // the binding's constructor path (pyx:164-186): get_quad_form, then Genus(q, symbols, seed)
+        std::vector<PrimeSymbol<int64_t>> symbols;
+        for (size_t i = 0; i < table->primes.size(); i++) symbols.push_back(PrimeSymbol<int64_t>{table->primes[i], 1, true});
+        QuadForm<int64_t> q = QuadForm<int64_t>::get_quad_form(symbols);
+        Genus<int64_t> built(q, symbols, table->seed);
+        out.push_back((int64_t)built.size());
+        out.push_back(built.table()->q == table->q && built.table()->s == table->s && built.table()->sinv == table->sinv &&
+                      built.table()->lut == table->lut && built.table()->scalar == table->scalar ? 1 : 0);
     }
     catch (const std::exception& e)
     {

@@ -59,3 +59,4 @@ def test_facade_matches_python_path(facade_binary, tables, tmp_path):
         assert a[pos] == 1, "bad-prime exception text"; pos += 1
         g.close()
     assert a[pos] == 130
+    assert a[pos + 1] == 130 and a[pos + 2] == 1, "Genus(q, symbols, seed) built through the facade differs from the reference's table"
