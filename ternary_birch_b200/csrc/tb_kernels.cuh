@@ -68,6 +68,89 @@ __global__ void prep_reps_kernel(GenusCtx gc, PrimeCtx pc, const u32 *base, int 
 }
 
 // ---------------------------------------------------------------------------
+// Conic base points on the device, one thread per representative, for the calls whose
+// result does not depend on WHICH rational point parametrises the p+1 lines (Hecke
+// matrices, eigenvalues: the set of lines is the same, only their order changes).  The
+// order-defining RNG-exact points (isometry_sequence) stay on the host.  Same construction
+// as QuadFormFp::isotropic_vector (QuadForm.h:847-907) with a deterministic scan instead of
+// random draws: take r with Q(1,r,0) != 0, then the first s whose line meets the conic in a
+// rational point, and solve the quadratic (Tonelli-Shanks with the launch's non-residue).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ u32 fp_sqrt_dev(u32 a, const PrimeCtx &pc, u32 nonres)
+{
+    const u32 p = pc.p;
+    if (a <= 1u) return a;
+    u32 odd = p - 1u;
+    int twos = 0;
+    while (!(odd & 1u)) { odd >>= 1; ++twos; }
+    if (twos == 1) return fp_pow(a, (p + 1u) / 4u, pc);
+    int m = twos;
+    u32 c = fp_pow(nonres, odd, pc), r = fp_pow(a, (odd + 1u) / 2u, pc), t = fp_pow(a, odd, pc);
+    while (t != 1u)
+    {
+        int i = 0;
+        for (u32 t1 = t; t1 != 1u; t1 = fp_mul(t1, t1, pc)) ++i;
+        u32 b = c;
+        for (int j = 0; j < m - i - 1; ++j) b = fp_mul(b, b, pc);
+        r = fp_mul(r, b, pc);
+        c = fp_mul(b, b, pc);
+        t = fp_mul(t, c, pc);
+        m = i;
+    }
+    return r;
+}
+
+__global__ void base_points_kernel(GenusCtx gc, PrimeCtx pc, u32 nonres, int rep_begin, int rows, u32 *base)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const i64 *cur = gc.cur + (size_t)(rep_begin + i) * TB_REC_WORDS;
+    const u32 p = pc.p;
+    PrimeCtx fc = pc;
+    fc.use_lut = 0;                                          // Fermat inverses: independent of the table build
+    if (p == 2u)
+    {
+        const u32 a = (u32)cur[0] & 1u, b = (u32)cur[1] & 1u, c = (u32)cur[2] & 1u;
+        const u32 f = (u32)cur[3] & 1u, g = (u32)cur[4] & 1u, h = (u32)cur[5] & 1u;
+        const u32 val[8] = {1u, c, b, b ^ f ^ c, a, a ^ g ^ c, a ^ h ^ b, a ^ b ^ c ^ f ^ g ^ h};
+        u32 found[3] = {0u, 0u, 0u};
+        int cnt = 0;
+        for (u32 v = 1; v < 8; ++v) if (val[v] == 0u && cnt < 3) found[cnt++] = v;
+        base[3 * i + 0] = found[0]; base[3 * i + 1] = found[1]; base[3 * i + 2] = found[2];
+        return;
+    }
+    const u32 a = fp_mod_i64(cur[0], fc), b = fp_mod_i64(cur[1], fc), c = fp_mod_i64(cur[2], fc);
+    const u32 f = fp_mod_i64(cur[3], fc), g = fp_mod_i64(cur[4], fc), h = fp_mod_i64(cur[5], fc);
+    const u32 half_exp = (p - 1u) / 2u;
+    for (u32 r = 0; r < p; ++r)
+    {
+        const u32 br = fp_mul(b, r, fc);
+        const u32 alpha = fp_add(fp_mul(fp_add(br, h, p), r, fc), a, p);              // Q(1, r, 0)
+        if (alpha == 0u) continue;
+        const u32 two_alpha_inv = fp_inv(fp_add(alpha, alpha, p), fc);
+        const u32 fr_g = fp_add(fp_mul(f, r, fc), g, p);
+        const u32 slope = fp_add(fp_add(br, br, p), h, p);
+        for (u32 s = 0; s < p; ++s)
+        {
+            const u32 beta = fp_add(fp_mul(slope, s, fc), fr_g, p);
+            const u32 gamma = fp_add(fp_mul(fp_add(fp_mul(b, s, fc), f, p), s, fc), c, p);   // Q(0, s, 1)
+            u32 four_ag = fp_mul(gamma, alpha, fc);
+            four_ag = fp_add(four_ag, four_ag, p);
+            four_ag = fp_add(four_ag, four_ag, p);
+            const u32 disc = fp_sub(fp_mul(beta, beta, fc), four_ag, p);
+            if (disc != 0u && fp_pow(disc, half_exp, fc) != 1u) continue;             // not a square
+            const u32 root = fp_sub(fp_sqrt_dev(disc, fc, nonres), beta, p);
+            const u32 x = fp_mul(root, two_alpha_inv, fc);
+            base[3 * i + 0] = x;
+            base[3 * i + 1] = fp_add(fp_mul(r, x, fc), s, p);
+            base[3 * i + 2] = 1u;
+            return;
+        }
+    }
+    base[3 * i + 0] = 0u; base[3 * i + 1] = 0u; base[3 * i + 2] = 1u;                 // unreachable for p not dividing disc
+}
+
+// ---------------------------------------------------------------------------
 // neighbors_kernel: one thread per (representative, t).
 //   MODE_PACKED   W[i] = (r << K) | spin                         Genus.h:617
 //   MODE_RECORDS  20 int64: line[3], reduced form[6], isometry[9], r, spin

@@ -215,7 +215,9 @@ struct PoolBuf {
 struct PrimeState {
     uint64_t p = 0;
     PrimeCtx pc;
-    std::vector<uint32_t> base;   // [N][3] host copy, all representatives
+    u32 nonres = 0;               // smallest quadratic non-residue mod p (device Tonelli-Shanks)
+    bool have_exact = false;
+    std::vector<uint32_t> base;   // [N][3] RNG-exact base points of all representatives (lazy)
 };
 
 struct tb_genus {
@@ -236,6 +238,7 @@ struct tb_genus {
     DevBuf<u32> d_invlut, d_base, d_W;
     DevBuf<RepPrime> d_rp;
     int rp_begin = -1, rp_rows = 0;
+    bool rp_exact = false;
     DevBuf<u64> d_err;
     DevBuf<int> d_tab;          // rowbase | rowfirst | rowcount   (row kernels)
     DevBuf<i64> d_nnz;          // nnz | nnzbase
@@ -522,12 +525,30 @@ static int setup_prime(tb_genus *g, uint64_t p)
         ++g_launches;
         TB_CUDA(cudaGetLastError());
     }
-    // base points of ALL representatives, in order, from one RNG stream
-    ps.base.resize(3 * (size_t)g->N);
-    HostFp F(p, g->seed);
-    for (int n = 0; n < g->N; ++n) base_point(F, &g->q[6 * (size_t)n], &ps.base[3 * (size_t)n]);
+    ps.have_exact = false;
+    ps.nonres = 0;
+    if (p > 2)
+    {
+        HostFp F(p, 1);
+        u32 z = 2;
+        while (F.legendre(z) != -1) ++z;
+        ps.nonres = z;
+    }
     ps.p = p;
     return TB_OK;
+}
+
+// RNG-exact base points of ALL representatives, in order, from one stream: the reference's
+// shared Fp across NeighborManager constructions.  They define the ORDER of the p+1 lines of
+// each representative, which only isometry_sequence / neighbor records expose.
+static void ensure_exact_base(tb_genus *g)
+{
+    PrimeState &ps = g->ps;
+    if (ps.have_exact) return;
+    ps.base.resize(3 * (size_t)g->N);
+    HostFp F(ps.p, g->seed);
+    for (int n = 0; n < g->N; ++n) base_point(F, &g->q[6 * (size_t)n], &ps.base[3 * (size_t)n]);
+    ps.have_exact = true;
 }
 
 // base points for an explicit list of representatives visited in ascending
@@ -561,12 +582,29 @@ static int stage_rows(tb_genus *g, const uint32_t *base, int rep_begin, int rows
     return TB_OK;
 }
 
-static int prepare_rows(tb_genus *g, int rep_begin, int rows)
+// exact = the reference's RNG-defined base points (host); otherwise any rational point of the
+// conic, found on the device (Hecke matrices and eigenvalues do not depend on the choice).
+static int prepare_rows(tb_genus *g, int rep_begin, int rows, bool exact)
 {
-    if (g->rp_begin == rep_begin && g->rp_rows == rows) return TB_OK;
-    if (int rc = stage_rows(g, &g->ps.base[3 * (size_t)rep_begin], rep_begin, rows)) return rc;
+    if (g->rp_begin == rep_begin && g->rp_rows == rows && g->rp_exact == exact) return TB_OK;
+    g->rp_begin = -1;
+    if (exact)
+    {
+        ensure_exact_base(g);
+        if (int rc = stage_rows(g, &g->ps.base[3 * (size_t)rep_begin], rep_begin, rows)) return rc;
+    }
+    else
+    {
+        TB_CUDA(g->d_base.reserve(3 * (size_t)rows));
+        TB_CUDA(g->d_rp.reserve(rows));
+        base_points_kernel<<<(rows + 127) / 128, 128, 0, g->stream>>>(g->gc, g->ps.pc, g->ps.nonres, rep_begin, rows, g->d_base.ptr);
+        prep_reps_kernel<<<(rows + 127) / 128, 128, 0, g->stream>>>(g->gc, g->ps.pc, g->d_base.ptr, rep_begin, rows, g->d_rp.ptr);
+        g_launches += 2;
+        TB_CUDA(cudaGetLastError());
+    }
     g->rp_begin = rep_begin;
     g->rp_rows = rows;
+    g->rp_exact = exact;
     return TB_OK;
 }
 
@@ -656,7 +694,7 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
         return TB_OK;
     }
 
-    if (int rc = prepare_rows(g, rb, rows)) return rc;
+    if (int rc = prepare_rows(g, rb, rows, false)) return rc;
     TB_CUDA(g->d_W.reserve((size_t)rows * P1));
 
     // small device-side tables for the row kernels
@@ -844,7 +882,7 @@ extern "C" int tb_neighbor_records(tb_genus *g, uint64_t p, int precise, int64_t
     if (int rc = setup_prime(g, p)) return rc;
     const int rows = (int)(rep_end - rep_begin);
     const size_t words = (size_t)rows * (p + 1) * 20;
-    if (int rc = prepare_rows(g, (int)rep_begin, rows)) return rc;
+    if (int rc = prepare_rows(g, (int)rep_begin, rows, true)) return rc;
     DevBuf<i64> d_rec;
     TB_CUDA(d_rec.reserve(words));
     TB_CUDA(cudaMemsetAsync(d_rec.ptr, 0, words * sizeof(i64), g->stream));
@@ -956,7 +994,7 @@ static int isoseq_fill(tb_isoseq *it)
     const int64_t max_records = 1 << 20;
     int rows = (int)std::max<int64_t>(1, std::min<int64_t>(g->N - it->next_rep, max_records / P1));
     const size_t words = (size_t)rows * P1 * 12;
-    if (int rc = prepare_rows(g, (int)it->next_rep, rows)) return rc;
+    if (int rc = prepare_rows(g, (int)it->next_rep, rows, true)) return rc;
     DevBuf<i64> d_rec;
     TB_CUDA(d_rec.reserve(words));
     if (int rc = launch_neighbors<MODE_ISOSEQ>(g, it->precise, (int)it->next_rep, rows, nullptr, d_rec.ptr)) { d_rec.release(); return rc; }
