@@ -704,7 +704,7 @@ __device__ __forceinline__ int reduce_loop_fp64(DReduce &d)
         // (form pairs swap by select on the ALU pipe, isometry columns arithmetically on the
         //  FP64 pipe: the two pipes are the kernel's co-limiters)
         {
-            const bool p = active && (a > b || (a == b && fabs(f) > fabs(g)));
+            const bool p = active & ((a > b) | ((a == b) & (fabs(f) > fabs(g))));
             const double m = p ? 1.0 : 0.0;
             dswap_sel(p, a, b); dswap_sel(p, f, g);
             dswap_fma(m, s11, s12); dswap_fma(m, s21, s22); dswap_fma(m, s31, s32);
@@ -712,7 +712,7 @@ __device__ __forceinline__ int reduce_loop_fp64(DReduce &d)
             sg1 = (p ? sg2 : sg1) ^ pm; sg2 = (p ? o1 : sg2) ^ pm; sg3 ^= pm;
         }
         {
-            const bool p = active && (b > c || (b == c && fabs(g) > fabs(h)));
+            const bool p = active & ((b > c) | ((b == c) & (fabs(g) > fabs(h))));
             const double m = p ? 1.0 : 0.0;
             dswap_sel(p, b, c); dswap_sel(p, g, h);
             dswap_fma(m, s12, s13); dswap_fma(m, s22, s23); dswap_fma(m, s32, s33);
@@ -720,7 +720,7 @@ __device__ __forceinline__ int reduce_loop_fp64(DReduce &d)
             sg2 = (p ? sg3 : sg2) ^ pm; sg3 = (p ? o2 : sg3) ^ pm; sg1 ^= pm;
         }
         {
-            const bool p = active && (a > b || (a == b && fabs(f) > fabs(g)));
+            const bool p = active & ((a > b) | ((a == b) & (fabs(f) > fabs(g))));
             const double m = p ? 1.0 : 0.0;
             dswap_sel(p, a, b); dswap_sel(p, f, g);
             dswap_fma(m, s11, s12); dswap_fma(m, s21, s22); dswap_fma(m, s31, s32);
@@ -729,27 +729,29 @@ __device__ __forceinline__ int reduce_loop_fp64(DReduce &d)
         }
 
         // sign normalisation                                          626-687
+        // Restated: if f g h > 0 (all nonzero, evenly many negative) flip the negative ones;
+        // otherwise flip the positive ones and, when that is an odd number of flips, also the
+        // first zero among f, g, h (column flips must come in pairs: det stays +p^2).
         {
             const bool fneg = f < 0.0, gneg = g < 0.0, hneg = h < 0.0;
-            const bool fz = f == 0.0, gz = g == 0.0, hz = h == 0.0;
-            const bool even_neg = !((fneg != gneg) != hneg);
-            const bool fgh = !fz && !gz && !hz && even_neg;
-            bool p1 = !fneg && !fz, p2 = !gneg && !gz, p3 = !hneg && !hz;
-            const bool odd = (p1 != p2) != p3;
-            p1 = p1 || (odd && fz);
-            p2 = p2 || (odd && !fz && gz);
-            p3 = p3 || (odd && !fz && !gz && hz);
-            const u32 n1 = (active && (fgh ? fneg : p1)) ? SIGN : 0u;
-            const u32 n2 = (active && (fgh ? gneg : p2)) ? SIGN : 0u;
-            const u32 n3 = (active && (fgh ? hneg : p3)) ? SIGN : 0u;
+            const bool fpos = f > 0.0, gpos = g > 0.0, hpos = h > 0.0;
+            const bool caseA = (f * g) * h > 0.0;
+            const bool oddB = !caseA & ((fpos != gpos) != hpos);
+            const bool fz = !fneg & !fpos, gz = !gneg & !gpos, hz = !hneg & !hpos;
+            const bool f1 = (caseA ? fneg : fpos) | (oddB & fz);
+            const bool f2 = (caseA ? gneg : gpos) | (oddB & !fz & gz);
+            const bool f3 = (caseA ? hneg : hpos) | (oddB & !fz & !gz & hz);
+            const u32 n1 = (active & f1) ? SIGN : 0u;
+            const u32 n2 = (active & f2) ? SIGN : 0u;
+            const u32 n3 = (active & f3) ? SIGN : 0u;
             f = xflip(f, n1); g = xflip(g, n2); h = xflip(h, n3);
             sg1 ^= n1; sg2 ^= n2; sg3 ^= n3;
         }
 
         // exit test                                                   689-690
         sum = (((a + b) + f) + g) + h;
-        const bool done = fabs(f) <= b && fabs(g) <= a && fabs(h) <= a && sum >= 0.0;
-        active = active && !done;
+        const bool done = (fabs(f) <= b) & (fabs(g) <= a) & (fabs(h) <= a) & (sum >= 0.0);
+        active = active & !done;
         act = active ? 1.0 : 0.0;
     }
 

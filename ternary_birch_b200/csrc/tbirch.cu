@@ -244,6 +244,10 @@ struct tb_genus {
     DevBuf<i64> d_nnz;          // nnz | nnzbase
     DevBuf<u64> d_lookback;     // [2^K][rows] look-back words + ticket (fused row kernel)
     bool allow_fused = true;
+    size_t device_bytes = 0;
+    // per-shard row bookkeeping of the last Hecke call (reused while the shard is unchanged)
+    int shard_begin = -1, shard_end = -1;
+    std::vector<int> shard_rows, shard_first;
     u64 *h_err = nullptr;       // pinned [2]
     i64 *h_nnz = nullptr;       // pinned [2 * 2^K]
     int *h_tab = nullptr;       // pinned [3 * 2^K]
@@ -449,6 +453,7 @@ extern "C" int tb_genus_upload(tb_genus *g, const tb_genus_desc *d)
     g->seed = d->seed;
     g->ps.p = 0;
     g->rp_begin = -1;
+    g->shard_begin = -1;
     return upload_table(g, d);
 }
 
@@ -673,17 +678,29 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     h->g = g; h->C = C; h->rep_begin = rb; h->rep_end = (int)rep_end;
     h->rows.assign(C, 0); h->rowfirst.assign(C, 0); h->rowbase.assign(C, 0);
     h->nnz.assign(C, 0); h->nnzbase.assign(C, 0);
+    if (g->shard_begin != rb || g->shard_end != (int)rep_end)
+    {
+        g->shard_rows.assign(C, 0);
+        g->shard_first.assign(C, 0);
+        for (int k = 0; k < C; ++k)
+        {
+            const int32_t *lut = &g->lut[(size_t)k * N];
+            int cnt = 0, first = -1;
+            for (int n = rb; n < (int)rep_end; ++n)
+                if (lut[n] != -1) { if (first < 0) first = lut[n]; ++cnt; }
+            g->shard_rows[k] = cnt;
+            g->shard_first[k] = first < 0 ? 0 : first;
+        }
+        g->shard_begin = rb;
+        g->shard_end = (int)rep_end;
+    }
     int total_ptr = 0;
     for (int k = 0; k < C; ++k)
     {
-        const int32_t *lut = &g->lut[(size_t)k * N];
-        int cnt = 0, first = -1;
-        for (int n = rb; n < (int)rep_end; ++n)
-            if (lut[n] != -1) { if (first < 0) first = lut[n]; ++cnt; }
-        h->rows[k] = cnt;
-        h->rowfirst[k] = first < 0 ? 0 : first;
+        h->rows[k] = g->shard_rows[k];
+        h->rowfirst[k] = g->shard_first[k];
         h->rowbase[k] = total_ptr;
-        total_ptr += cnt + 1;
+        total_ptr += h->rows[k] + 1;
     }
     TB_CUDA(h->d_indptr.reserve(total_ptr, g->stream));
     TB_CUDA(cudaMemsetAsync(h->d_indptr.ptr, 0, (size_t)total_ptr * sizeof(int), g->stream));
@@ -713,8 +730,13 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
         cap[k] = (int64_t)h->rows[k] * std::min<int64_t>(P1, g->dims[k]);
         cap_total += cap[k];
     }
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
+    if (g->device_bytes == 0)
+    {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);                // slow call: once per genus
+        g->device_bytes = total_b;
+    }
+    const size_t total_b = g->device_bytes;
     const bool fused = g->allow_fused && (size_t)cap_total * 8 <= std::min<size_t>((size_t)48 << 30, total_b / 3);
 
     RowLaunch R;
