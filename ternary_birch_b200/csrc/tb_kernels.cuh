@@ -426,12 +426,24 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
     const int jbeg = min(ncols, w * B), jend = min(ncols, jbeg + B);
     int *warp_cnt = warp_sums;                                 // [8][32], reuses the scan scratch
     __shared__ int s_npos[8];
+    __shared__ u64 s_partab[1024];                             // parity table of the current conductor chunk (K <= 10)
+    const bool use_tab = L.K <= 10;
 
     for (int kc = 0; kc < C; kc += 8)
     {
         const int nk = min(8, C - kc);
         __syncthreads();
         if (tid < 8) s_npos[tid] = tid < nk ? L.lut[(size_t)(kc + tid) * L.N + n] : -1;
+        if (use_tab)
+        {
+            for (int sp = tid; sp < C; sp += nt)
+            {
+                u64 v = 0;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) v |= (u64)(__popc((u32)sp & (u32)(kc + kk)) & 1) << (8 * kk);
+                s_partab[sp] = v;
+            }
+        }
         __syncthreads();
 
         int cnt[8];
@@ -474,15 +486,27 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
                     b = start[j + 1];
                     e = (j + 1 < ncols) ? start[j + 2] : nvalid;
                 }
-                // odd[kk] = #{entries of the run with chi_k = -1}
+                // odd[kk] = #{entries of the run with chi_k = -1}.  Run lengths vary (the tail
+                // iterations run with a handful of lanes), so the per-entry work is one table
+                // add: s_partab[spin] holds the eight parities spread over the bytes of a u64.
                 int odd[8];
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) odd[kk] = 0;
-                for (int i = b; i < e; ++i)
+                if (use_tab && e - b < 256)
                 {
-                    const u32 sp = spins[i];
+                    u64 acc = 0;
+                    for (int i = b; i < e; ++i) acc += s_partab[spins[i]];
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) odd[kk] += __popc(sp & (u32)(kc + kk)) & 1;
+                    for (int kk = 0; kk < 8; ++kk) odd[kk] = (int)((acc >> (8 * kk)) & 0xffull);
+                }
+                else
+                {
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) odd[kk] = 0;
+                    for (int i = b; i < e; ++i)
+                    {
+                        const u32 sp = spins[i];
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) odd[kk] += __popc(sp & (u32)(kc + kk)) & 1;
+                    }
                 }
                 // row positions of this column for the eight conductors: 32 contiguous bytes
                 int rp[8];

@@ -748,13 +748,13 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     R.nnzbase = d_nnz.ptr + C;
     R.nnz_out = d_nnz.ptr;
     const size_t smem = rows_smem_bytes(N, P1);
-    if (smem > 226 * 1024)
+    if (smem > 218 * 1024)
         return fail(TB_ERR_RUNTIME, "libtbirch: row accumulation needs more shared memory than one SM has for this (N, p)");
     const int threads = (int)std::min<u32>(512, std::max<u32>(64, (P1 + 31) / 32 * 32));
     static bool attrs_set = false;
     if (!attrs_set)
     {
-        const int optin = 226 * 1024;   // 227 KB per CTA minus the kernels' static shared memory
+        const int optin = 218 * 1024;   // 227 KB per CTA minus the kernels' static shared memory (8 KB parity table)
         TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
