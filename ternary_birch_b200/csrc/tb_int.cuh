@@ -195,15 +195,21 @@ __device__ __forceinline__ W64 ref_quotient(W64 num, W64 den)
 }
 
 // ---------------------------------------------------------------------------
-// C128: overflow-checked signed 128-bit.
+// I128<CHK>: two-limb signed 128-bit.  C128 = I128<true> checks every operation for
+// overflow (sticky CTA flag); U128 = I128<false> is the same arithmetic without the
+// checks, used when the host has PROVEN from the launch's bounds (max coefficient, p,
+// isometry sizes) that no intermediate can leave 127 bits -- see precise_bounds_ok().
 // ---------------------------------------------------------------------------
-struct C128 {
+template <bool CHK>
+struct I128 {
+    typedef I128<CHK> C128;   // local alias: the body below is written in terms of C128
+    static __device__ __forceinline__ void ovf() { if (CHK) ovf(); }
     u64 lo;
     i64 hi;
 
-    __device__ __forceinline__ C128() {}
-    __device__ __forceinline__ C128(i64 x) : lo((u64)x), hi(x < 0 ? -1ll : 0ll) {}
-    __device__ __forceinline__ C128(u64 l, i64 h) : lo(l), hi(h) {}
+    __device__ __forceinline__ I128() {}
+    __device__ __forceinline__ I128(i64 x) : lo((u64)x), hi(x < 0 ? -1ll : 0ll) {}
+    __device__ __forceinline__ I128(u64 l, i64 h) : lo(l), hi(h) {}
     __device__ __forceinline__ static C128 from_i64(i64 x) { return C128(x); }
 
     __device__ __forceinline__ i64 low64() const { return (i64)lo; }
@@ -216,14 +222,14 @@ struct C128 {
         u64 l = a.lo + b.lo;
         u64 c = l < a.lo ? 1ull : 0ull;
         i64 h = (i64)((u64)a.hi + (u64)b.hi + c);
-        if (((a.hi ^ h) & (b.hi ^ h)) < 0) raise_overflow();
+        if (((a.hi ^ h) & (b.hi ^ h)) < 0) ovf();
         return C128(l, h);
     }
     friend __device__ __forceinline__ C128 operator-(C128 a)
     {
         u64 l = 0ull - a.lo;
         i64 h = (i64)(0ull - (u64)a.hi - (a.lo != 0 ? 1ull : 0ull));
-        if (a.hi < 0 && h < 0 && a.lo == 0) raise_overflow();   // -(-2^127)
+        if (a.hi < 0 && h < 0 && a.lo == 0) ovf();   // -(-2^127)
         return C128(l, h);
     }
     friend __device__ __forceinline__ C128 operator-(C128 a, C128 b)
@@ -231,11 +237,18 @@ struct C128 {
         u64 l = a.lo - b.lo;
         u64 br = a.lo < b.lo ? 1ull : 0ull;
         i64 h = (i64)((u64)a.hi - (u64)b.hi - br);
-        if (((a.hi ^ b.hi) & (a.hi ^ h)) < 0) raise_overflow();
+        if (((a.hi ^ b.hi) & (a.hi ^ h)) < 0) ovf();
         return C128(l, h);
     }
     friend __device__ __forceinline__ C128 operator*(C128 a, C128 b)
     {
+        if (!CHK)
+        {
+            // low 128 bits of the product (exact: the host proved it fits)
+            const u64 l = a.lo * b.lo;
+            const u64 h = __umul64hi(a.lo, b.lo) + a.lo * (u64)b.hi + (u64)a.hi * b.lo;
+            return C128(l, (i64)h);
+        }
         if (a.fits_i64() && b.fits_i64())
         {
             // |a|,|b| <= 2^63  =>  |ab| <= 2^126: always representable
@@ -263,7 +276,7 @@ struct C128 {
     }
     __device__ __forceinline__ static C128 from_mag(u64 mh, u64 ml, bool neg)
     {
-        if ((i64)mh < 0) { raise_overflow(); }
+        if ((i64)mh < 0) { ovf(); }
         C128 r(ml, (i64)mh);
         return neg ? -r : r;
     }
@@ -275,50 +288,54 @@ struct C128 {
         a.umag(ah, al);
         b.umag(bh, bl);
         bool neg = (a.hi < 0) != (b.hi < 0);
-        if (ah != 0 && bh != 0) { raise_overflow(); return C128(0); }
+        if (ah != 0 && bh != 0) { ovf(); return C128(0); }
         u64 cross_hi = ah ? __umul64hi(ah, bl) : __umul64hi(al, bh);
         u64 cross = ah ? ah * bl : al * bh;
         u64 l = al * bl;
         u64 h = __umul64hi(al, bl);
         u64 top = h + cross;
-        if (cross_hi != 0 || top < h || (i64)top < 0) { raise_overflow(); return C128(0); }
+        if (cross_hi != 0 || top < h || (i64)top < 0) { ovf(); return C128(0); }
         C128 r(l, (i64)top);
         return neg ? -r : r;
     }
 };
 
-__device__ __forceinline__ C128 trunc_rem(C128 x, const InvDiv &iv)
+template <bool CHK>
+__device__ __forceinline__ I128<CHK> trunc_rem(I128<CHK> x, const InvDiv &iv)
 {
     u64 mh, ml, qh, ql, r;
     x.umag(mh, ml);
     if (mh == 0) udivmod(ml, iv, r);
     else udivmod128(mh, ml, iv, qh, ql, r);
-    C128 out((i64)r);                      // r < d < 2^63
+    I128<CHK> out((i64)r);                      // r < d < 2^63
     return x.hi < 0 ? -out : out;
 }
-__device__ __forceinline__ C128 trunc_div(C128 x, const InvDiv &iv)
+template <bool CHK>
+__device__ __forceinline__ I128<CHK> trunc_div(I128<CHK> x, const InvDiv &iv)
 {
     u64 mh, ml, qh, ql, r;
     x.umag(mh, ml);
     if (mh == 0) { qh = 0; ql = udivmod(ml, iv, r); }
     else udivmod128(mh, ml, iv, qh, ql, r);
-    return C128::from_mag(qh, ql, x.hi < 0);
+    return I128<CHK>::from_mag(qh, ql, x.hi < 0);
 }
-__device__ __forceinline__ bool strip_factor(C128 &x, const InvDiv &iv)
+template <bool CHK>
+__device__ __forceinline__ bool strip_factor(I128<CHK> &x, const InvDiv &iv)
 {
     u64 mh, ml, qh, ql, r;
     x.umag(mh, ml);
     if (mh == 0) { qh = 0; ql = udivmod(ml, iv, r); }
     else udivmod128(mh, ml, iv, qh, ql, r);
     if (r != 0) return false;
-    x = C128::from_mag(qh, ql, x.hi < 0);
+    x = I128<CHK>::from_mag(qh, ql, x.hi < 0);
     return true;
 }
 
 // floor(num/den) for the non-negative numerator / positive denominator that
 // reduce forms on a positive definite ternary form (QuadForm.cpp:104-117 uses
 // mpz_fdiv_q).  Wider operands take a shift-subtract division.
-__device__ __noinline__ C128 quotient_slow(C128 num, C128 den)
+template <bool CHK>
+__device__ __noinline__ I128<CHK> quotient_slow(I128<CHK> num, I128<CHK> den)
 {
     // binary long division on magnitudes (num >= 0, den > 0 established by the caller)
     u64 nh = (u64)num.hi, nl = num.lo, dh = (u64)den.hi, dl = den.lo;
@@ -336,10 +353,11 @@ __device__ __noinline__ C128 quotient_slow(C128 num, C128 den)
             if (bit >= 64) qh |= 1ull << (bit - 64); else ql |= 1ull << bit;
         }
     }
-    return C128(ql, (i64)qh);
+    return I128<CHK>(ql, (i64)qh);
 }
 
-__device__ __forceinline__ C128 ref_quotient(C128 num, C128 den)
+template <bool CHK>
+__device__ __forceinline__ I128<CHK> ref_quotient(I128<CHK> num, I128<CHK> den)
 {
     if (num.hi == 0 && den.hi == 0 && (i64)num.lo >= 0 && (i64)den.lo > 0 && num.lo < (1ull << 50))
     {
@@ -348,16 +366,19 @@ __device__ __forceinline__ C128 ref_quotient(C128 num, C128 den)
         i64 r = n - q * d;
         if (r < 0) { q -= 1; r += d; }
         if (r >= d) { q += 1; }
-        return C128(q);
+        return I128<CHK>(q);
     }
     if (num.is_neg() || den.is_neg() || den.is_zero())
     {
         // not reachable with exact arithmetic on a positive definite form
-        raise_overflow();
-        return C128(0);
+        I128<CHK>::ovf();
+        return I128<CHK>(0);
     }
-    if (num.hi == 0 && den.hi == 0) return C128(num.lo / den.lo, 0);
+    if (num.hi == 0 && den.hi == 0) return I128<CHK>(num.lo / den.lo, 0);
     return quotient_slow(num, den);
 }
+
+typedef I128<true> C128;
+typedef I128<false> U128;
 
 }  // namespace tb

@@ -172,8 +172,13 @@ struct NbrLaunch {
     u64 *err;
 };
 
+// register budget per integer mode: 72 registers (7 CTAs/SM) suit the int64 kernel, the
+// two-limb kernels need ~3x the live state
+template <class Z> struct NbrBlocks { static const int value = 3; };
+template <> struct NbrBlocks<W64> { static const int value = TB_NBR_MINBLOCKS; };
+
 template <class Z, int MODE>
-__global__ void __launch_bounds__(TB_NBR_THREADS, TB_NBR_MINBLOCKS)
+__global__ void __launch_bounds__(TB_NBR_THREADS, NbrBlocks<Z>::value)
 neighbors_kernel(const __grid_constant__ GenusCtx gc, const __grid_constant__ PrimeCtx pc,
                  const __grid_constant__ NbrLaunch L)
 {

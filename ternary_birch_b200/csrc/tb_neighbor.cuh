@@ -7,7 +7,7 @@
 //   genus_lookup      open-addressing probe          HashMap.h:68-89, QuadForm.cpp:779-803
 //   spinor_norm       spinor/Kronecker class         Spinor.h:19-66, Genus.h:582-615
 // One thread owns one neighbor.  All of it is templated on the integer mode Z
-// (W64 | C128, tb_int.cuh).
+// (W64 | C128 | U128, tb_int.cuh).
 #pragma once
 
 #include "tb_int.cuh"
@@ -618,7 +618,8 @@ __device__ __forceinline__ double dshear_t(double a, double h, double den, doubl
 // 2^50 magnitude test on an int64
 __device__ __forceinline__ bool small50(i64 v) { return (u64)(v + (1ll << 50)) < (1ull << 51); }
 __device__ __forceinline__ bool fits50(W64 x) { return small50(x.v); }
-__device__ __forceinline__ bool fits50(C128 x) { return x.fits_i64() && small50((i64)x.lo); }
+template <bool CHK>
+__device__ __forceinline__ bool fits50(I128<CHK> x) { return x.fits_i64() && small50((i64)x.lo); }
 
 struct DReduce {
     double a, b, c, f, g, h;

@@ -228,6 +228,8 @@ struct tb_genus {
     std::vector<int32_t> lut;
 
     double lambda_min = 1.0;    // lower bound of the smallest Gram eigenvalue over all representatives
+    double log2_coef = 0, log2_iso = 0, log2_scalar = 0;   // log2 of the largest |q|, |s| / |sinv|, scalar entries
+    double log2_mother = 0;                                // log2 of the largest |coefficient| of representative 0
     cudaStream_t stream = 0;
     DevBuf<i64> d_cur, d_rep, d_disc;
     DevBuf<int> d_slots, d_lut, d_lutT;
@@ -244,6 +246,7 @@ struct tb_genus {
     DevBuf<i64> d_nnz;          // nnz | nnzbase
     DevBuf<u64> d_lookback;     // [2^K][rows] look-back words + ticket (fused row kernel)
     bool allow_fused = true;
+    bool force_checked = false;   // TBIRCH_FORCE_CHECKED: always run the checked C128 kernel in precise mode
     size_t device_bytes = 0;
     // per-shard row bookkeeping of the last Hecke call (reused while the shard is unchanged)
     int shard_begin = -1, shard_end = -1;
@@ -349,6 +352,20 @@ static int upload_table(tb_genus *g, const tb_genus_desc *d)
         lam = std::min(lam, 0.25 * det4 / (tr * tr));
     }
     g->lambda_min = definite ? lam * 0.5 : 0.0;   // 0 disables the FP64 reduce loop
+    {
+        double mq = 1, ms = 1, md = 1;
+        for (int n = 0; n < N; ++n)
+        {
+            const i64 *c = cur + (size_t)n * TB_REC_WORDS, *r = rep + (size_t)n * TB_REC_WORDS;
+            for (int i = 0; i < 6; ++i) mq = std::max(mq, fabs((double)c[i]));
+            md = std::max(md, fabs((double)c[6]));
+            for (int i = 7; i < 16; ++i) ms = std::max(ms, std::max(fabs((double)c[i]), fabs((double)r[i])));
+        }
+        g->log2_coef = log2(mq); g->log2_iso = log2(ms); g->log2_scalar = log2(md);
+        double mm = 1;
+        for (int i = 0; i < 6; ++i) mm = std::max(mm, fabs((double)cur[i]));
+        g->log2_mother = log2(mm);
+    }
     // open-addressing table of representatives: 2 * 2^ceil(log2 N) slots (>= 32), linear probing,
     // keyed by the reference's FNV hash of the six coefficients (HashMap.h:10-24, QuadForm.cpp:779-803).
     for (u32 i = 0; i < slots; ++i) table[i] = -1;
@@ -422,7 +439,8 @@ extern "C" int tb_genus_create(const tb_genus_desc *d, tb_genus **out)
     g->q.assign(d->q, d->q + 6 * (size_t)g->N);
     g->lut.assign(d->lut, d->lut + ((size_t)g->N << g->K));
     if (int rc = upload_table(g.get(), d)) return rc;
-    g->allow_fused = getenv("TBIRCH_TWO_PASS_ROWS") == nullptr;   // debugging / A-B switch
+    g->allow_fused = getenv("TBIRCH_TWO_PASS_ROWS") == nullptr;   // debugging / A-B switches
+    g->force_checked = getenv("TBIRCH_FORCE_CHECKED") != nullptr;
     TB_CUDA(g->d_err.reserve(2));
     TB_CUDA(g->d_tab.reserve(3 * (size_t)C));
     TB_CUDA(g->d_nnz.reserve(2 * (size_t)C));
@@ -613,6 +631,31 @@ static int prepare_rows(tb_genus *g, int rep_begin, int rows, bool exact)
     return TB_OK;
 }
 
+// May the precise mode drop its overflow checks for this prime?  Conservative magnitude
+// bounds (log2) on everything the 128-bit pipeline forms, from the genus table and p:
+//   build_neighbor   every intermediate is below 8 A p^4          (A = max |coefficient|)
+//   reduce           FP64 loop enabled => all loop values < 2^53; isometry entries < 2^52
+//   reduced isometry columns v satisfy Q_rep(v) = p^2 * (coefficient of a genus representative),
+//                    so |entry| <= p sqrt(A / lambda_min)
+//   compose          |cur.s * s * rep.sinv| entries < 9 S^2 p sqrt(A / lambda_min)   (S = max |s|, |sinv|)
+//   Spinor::norm     composed case: mother-form minors (<= 4 A0^2) times composed entries / denominators;
+//                    r == n case: minors of a representative (<= 4 A^2) times neighbor-isometry entries
+//   denominator      p * D^2                                       (D = max scalar)
+// When all stay far below 2^127 the unchecked U128 arithmetic is exact, i.e. equal to GMP's.
+static bool precise_bounds_ok(const tb_genus *g)
+{
+    const PrimeCtx &pc = g->ps.pc;
+    if (!pc.fp64_reduce) return false;
+    const double lp = log2((double)pc.p);
+    const double build = 3 + g->log2_coef + 4 * lp;
+    const double iso = 1 + lp + 0.5 * (g->log2_coef - log2(g->lambda_min));
+    const double comp = 4 + 2 * g->log2_iso + iso;
+    const double denom = lp + 2 * g->log2_scalar;
+    const double spin_comp = 6 + 2 * g->log2_mother + std::max(comp, denom);
+    const double spin_self = 6 + 2 * g->log2_coef + std::max(iso, lp);
+    return build < 120 && comp < 120 && denom < 120 && spin_comp < 120 && spin_self < 120;
+}
+
 template <int MODE>
 static int launch_neighbors(tb_genus *g, int precise, int rep_begin, int rows, u32 *W, i64 *records)
 {
@@ -630,7 +673,9 @@ static int launch_neighbors(tb_genus *g, int precise, int rep_begin, int rows, u
     const u64 blocks = (L.total + TB_NBR_THREADS - 1) / TB_NBR_THREADS;
     if (blocks > 0x7fffffffull) return fail(TB_ERR_RUNTIME, "libtbirch: launch too large");
     TB_CUDA(cudaMemsetAsync(g->d_err.ptr, 0xff, 2 * sizeof(u64), g->stream));
-    if (precise)
+    if (precise && precise_bounds_ok(g) && !g->force_checked)
+        neighbors_kernel<U128, MODE><<<(unsigned)blocks, TB_NBR_THREADS, 0, g->stream>>>(g->gc, g->ps.pc, L);
+    else if (precise)
         neighbors_kernel<C128, MODE><<<(unsigned)blocks, TB_NBR_THREADS, 0, g->stream>>>(g->gc, g->ps.pc, L);
     else
         neighbors_kernel<W64, MODE><<<(unsigned)blocks, TB_NBR_THREADS, 0, g->stream>>>(g->gc, g->ps.pc, L);
