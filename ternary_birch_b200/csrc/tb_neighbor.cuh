@@ -37,6 +37,8 @@ struct PrimeCtx {
     u32 use_lut;
     u32 fp64_reduce;  // host-verified: isometry entries stay below 2^52 in the FP64 reduce loop
     u32 m32;          // floor(2^32 / p) when p < 2^16 (32-bit Barrett), else 0
+    u32 narrow_trace; // two-limb modes: composed isometry / denominator proven below 2^61 (64-bit trace)
+    u32 pad2;
     u64 pp;
     InvDiv dp;        // division by p
     InvDiv dpp;       // division by p^2
@@ -963,6 +965,9 @@ __device__ __forceinline__ Iso<Z> load_iso(const i64 *m)
 // ---------------------------------------------------------------------------
 enum NeighborStatus { NBR_OK = 0, NBR_OVERFLOW = 1, NBR_NOT_FOUND = 2 };
 
+template <class Z> struct IsWide { static const bool value = true; };
+template <> struct IsWide<W64> { static const bool value = false; };
+
 template <class Z>
 struct Neighbor {
     u32 vx, vy, vz;   // isotropic line
@@ -1016,6 +1021,30 @@ __device__ __forceinline__ int one_neighbor(int n, u32 t, const RepPrime &rp, co
         return status;
     }
     const i64 *rep = gc.rep + (size_t)r * TB_REC_WORDS;      // Genus.h:588-615
+    if (IsWide<Z>::value && pc.narrow_trace && !want_comp &&
+        o.s.a11.fits_i64() && o.s.a12.fits_i64() && o.s.a13.fits_i64() && o.s.a21.fits_i64() && o.s.a22.fits_i64() &&
+        o.s.a23.fits_i64() && o.s.a31.fits_i64() && o.s.a32.fits_i64() && o.s.a33.fits_i64())
+    {
+        // Two-limb modes: the composed isometry cur.s * s * rep.sinv maps the mother form to
+        // itself with scalar denom, so its entries are below denom * sqrt(c0 / lambda_min(mother));
+        // the host set narrow_trace because that (and denom) stay below 2^61.  Trace and
+        // denominator are then exact in wrap-around 64-bit ring arithmetic.
+        Iso<W64> s64;
+        s64.a11 = W64(o.s.a11.low64()); s64.a12 = W64(o.s.a12.low64()); s64.a13 = W64(o.s.a13.low64());
+        s64.a21 = W64(o.s.a21.low64()); s64.a22 = W64(o.s.a22.low64()); s64.a23 = W64(o.s.a23.low64());
+        s64.a31 = W64(o.s.a31.low64()); s64.a32 = W64(o.s.a32.low64()); s64.a33 = W64(o.s.a33.low64());
+        const Iso<W64> cs64 = load_iso<W64>(cur + 7), ri64 = load_iso<W64>(rep + 7);
+        const Iso<W64> m64 = iso_mul(cs64, s64);
+        const W64 tr64 = m64.a11 * ri64.a11 + m64.a12 * ri64.a21 + m64.a13 * ri64.a31 +
+                         m64.a21 * ri64.a12 + m64.a22 * ri64.a22 + m64.a23 * ri64.a32 +
+                         m64.a31 * ri64.a13 + m64.a32 * ri64.a23 + m64.a33 * ri64.a33;
+        const W64 den64 = W64((i64)pc.p) * W64(__ldg(cur + 6)) * W64(__ldg(rep + 6));
+        if (tr64 != -den64)
+        {
+            o.spin = prime_parities(tr64 + den64, gc);
+            return status;
+        }
+    }
     const Iso<Z> cs = load_iso<Z>(cur + 7);
     const Iso<Z> rsinv = load_iso<Z>(rep + 7);
     const Iso<Z> m = iso_mul(cs, o.s);

@@ -230,6 +230,7 @@ struct tb_genus {
     double lambda_min = 1.0;    // lower bound of the smallest Gram eigenvalue over all representatives
     double log2_coef = 0, log2_iso = 0, log2_scalar = 0;   // log2 of the largest |q|, |s| / |sinv|, scalar entries
     double log2_mother = 0;                                // log2 of the largest |coefficient| of representative 0
+    double mother_lambda = 0;                              // lower bound of the mother form's smallest Gram eigenvalue
     cudaStream_t stream = 0;
     DevBuf<i64> d_cur, d_rep, d_disc;
     DevBuf<int> d_slots, d_lut, d_lutT;
@@ -350,6 +351,7 @@ static int upload_table(tb_genus *g, const tb_genus_desc *d)
         const double tr = a + b + cc;
         if (!(a > 0 && b > 0 && cc > 0 && det4 > 0 && 4.0 * a * b - h * h > 0)) { definite = false; break; }
         lam = std::min(lam, 0.25 * det4 / (tr * tr));
+        if (n == 0) g->mother_lambda = 0.5 * 0.25 * det4 / (tr * tr);
     }
     g->lambda_min = definite ? lam * 0.5 : 0.0;   // 0 disables the FP64 reduce loop
     {
@@ -537,6 +539,11 @@ static int setup_prime(tb_genus *g, uint64_t p)
     pc.dpp = make_invdiv(p * p);
     pc.use_lut = (p > 2 && p < (1ull << 22)) ? 1u : 0u;
     pc.m32 = (p > 2 && p < (1ull << 16)) ? (u32)((1ull << 32) / p) : 0u;
+    // 64-bit trace in the two-limb modes: |composed entry| <= denom * sqrt(c0 / lambda_min(mother))
+    {
+        const double lden = log2((double)p) + 2 * g->log2_scalar;
+        pc.narrow_trace = (g->mother_lambda > 0 && lden + 0.5 * (g->log2_mother - log2(g->mother_lambda)) + 2 < 61) ? 1u : 0u;
+    }
     // FP64 reduce loop: isometry entries are bounded by p * sqrt(M / lambda_min) with M < 2^50 the
     // loop's entry guard on the coefficients (tb_neighbor.cuh); require that bound below 2^52.
     pc.fp64_reduce = ((double)p * sqrt(1125899906842624.0 / g->lambda_min) < 4503599627370496.0) ? 1u : 0u;
