@@ -38,11 +38,12 @@ __global__ void inverse_lut_kernel(PrimeCtx pc, u32 *lut)
 // Per-representative constants for this prime.  base[n] = (x0, y0, z0) comes
 // from the host (it consumes the reference's sequential RNG stream).
 // ---------------------------------------------------------------------------
-__global__ void prep_reps_kernel(GenusCtx gc, PrimeCtx pc, const u32 *base, int rep_begin, int rows, RepPrime *out)
+__global__ void prep_reps_kernel(GenusCtx gc, PrimeCtx pc, const u32 *base, int rep_begin, int rows, RepPrime *out,
+                                 const int *rep_list = nullptr)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
-    const int n = rep_begin + i;
+    const int n = rep_list ? rep_list[i] : rep_begin + i;
     const i64 *cur = gc.cur + (size_t)n * TB_REC_WORDS;
     const u32 p = pc.p;
     RepPrime rp;
@@ -170,6 +171,7 @@ struct NbrLaunch {
     u32 *W;
     i64 *records;
     u64 *err;
+    const int *rep_list;   // optional: row -> representative (eigenvalue path), else rep_begin + row
 };
 
 // register budget per integer mode: 72 registers (7 CTAs/SM) suit the int64 kernel, the
@@ -194,7 +196,7 @@ neighbors_kernel(const __grid_constant__ GenusCtx gc, const __grid_constant__ Pr
         u64 t64;
         const u64 row = udivmod(i, L.dP1, t64);
         const u32 t = (u32)t64;
-        const int n = L.rep_begin + (int)row;
+        const int n = L.rep_list ? L.rep_list[row] : L.rep_begin + (int)row;
         const RepPrime rp = L.rp[row];
 
         Neighbor<Z> o;
@@ -631,20 +633,23 @@ __global__ void dense_scatter_kernel(const int *indptr, const int *data, const i
 }
 
 // ---------------------------------------------------------------------------
-// Eigenvalue accumulation for one representative.  Genus.h:490-499.
-//   out[v] += chi_{cond[v]}(spin_t) * vecs[v][r_t]   for every vector listed in sel[]
+// Eigenvalue accumulation, all set-cover representatives in one launch.  Genus.h:490-499.
+//   out[v] += chi_{cond[v]}(spin) * vecs[v][r]   over the neighbors of rep_of_vec[v]
+// grid.y = row (one representative of rep_list per row), threads over t.
 // ---------------------------------------------------------------------------
 __global__ void eigen_dot_kernel(const u32 *W, u32 P1, int K, int N, const int *vecs, const i64 *cond,
-                                 const int *sel, int nsel, int *out)
+                                 const int *rep_of_vec, int V, const int *rep_list, int *out)
 {
+    const int row = blockIdx.y;
+    const int n = rep_list[row];
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = t < P1;
-    u32 w = live ? W[t] : 0u;
+    const u32 w = live ? W[(size_t)row * P1 + t] : 0u;
     const u32 r = w >> K, spin = w & ((1u << K) - 1u);
     live = live && r < (u32)N;
-    for (int s = 0; s < nsel; ++s)
+    for (int v = 0; v < V; ++v)
     {
-        const int v = sel[s];
+        if (rep_of_vec[v] != n) continue;                    // block-uniform
         int term = 0;
         if (live)
         {

@@ -252,6 +252,8 @@ struct tb_genus {
     // per-shard row bookkeeping of the last Hecke call (reused while the shard is unchanged)
     int shard_begin = -1, shard_end = -1;
     std::vector<int> shard_rows, shard_first;
+    char *h_stage[2] = {nullptr, nullptr};   // pinned staging for copies into pageable host memory
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     u64 *h_err = nullptr;       // pinned [2]
     i64 *h_nnz = nullptr;       // pinned [2 * 2^K]
     int *h_tab = nullptr;       // pinned [3 * 2^K]
@@ -483,6 +485,7 @@ extern "C" void tb_genus_destroy(tb_genus *g)
     g->d_cur.release(); g->d_rep.release(); g->d_disc.release(); g->d_slots.release(); g->d_lut.release(); g->d_lutT.release();
     g->d_invlut.release(); g->d_base.release(); g->d_W.release(); g->d_rp.release(); g->d_err.release();
     g->d_tab.release(); g->d_nnz.release(); g->d_lookback.release();
+    for (int i = 0; i < 2; ++i) { if (g->h_stage[i]) cudaFreeHost(g->h_stage[i]); if (g->ev_stage[i]) cudaEventDestroy(g->ev_stage[i]); }
     if (g->h_err) cudaFreeHost(g->h_err);
     if (g->h_nnz) cudaFreeHost(g->h_nnz);
     if (g->h_tab) cudaFreeHost(g->h_tab);
@@ -664,7 +667,8 @@ static bool precise_bounds_ok(const tb_genus *g)
 }
 
 template <int MODE>
-static int launch_neighbors(tb_genus *g, int precise, int rep_begin, int rows, u32 *W, i64 *records)
+static int launch_neighbors(tb_genus *g, int precise, int rep_begin, int rows, u32 *W, i64 *records,
+                            const int *rep_list = nullptr)
 {
     NbrLaunch L;
     memset(&L, 0, sizeof(L));
@@ -677,6 +681,7 @@ static int launch_neighbors(tb_genus *g, int precise, int rep_begin, int rows, u
     L.W = W;
     L.records = records;
     L.err = g->d_err.ptr;
+    L.rep_list = rep_list;
     const u64 blocks = (L.total + TB_NBR_THREADS - 1) / TB_NBR_THREADS;
     if (blocks > 0x7fffffffull) return fail(TB_ERR_RUNTIME, "libtbirch: launch too large");
     TB_CUDA(cudaMemsetAsync(g->d_err.ptr, 0xff, 2 * sizeof(u64), g->stream));
@@ -891,14 +896,57 @@ extern "C" int64_t tb_hecke_rows(const tb_hecke *h, int64_t k) { return h->rows[
 extern "C" int64_t tb_hecke_row_begin(const tb_hecke *h, int64_t k) { return h->rowfirst[k]; }
 extern "C" int64_t tb_hecke_nnz(const tb_hecke *h, int64_t k) { return h->nnz[k]; }
 
+// Device -> caller copy.  Device or pinned destinations take one cudaMemcpyAsync; pageable
+// host memory (a std::vector, a numpy array) would make the driver stage through its own small
+// buffer at a few GB/s, so it is pipelined through two pinned 32 MB buffers instead: the DMA
+// of chunk i overlaps the host memcpy of chunk i-1.
+static const size_t TB_STAGE_BYTES = (size_t)32 << 20;
+
+static int copy_out(tb_genus *g, void *dst, const void *src_dev, size_t bytes)
+{
+    if (bytes == 0) return TB_OK;
+    cudaStream_t st = g->stream;
+    cudaPointerAttributes attr;
+    const bool known = cudaPointerGetAttributes(&attr, dst) == cudaSuccess;
+    cudaGetLastError();
+    if (known && attr.type != cudaMemoryTypeUnregistered)
+    {
+        TB_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDefault, st));
+        return TB_OK;                                  // caller synchronises
+    }
+    for (int i = 0; i < 2; ++i)
+        if (!g->h_stage[i])
+        {
+            TB_CUDA(cudaMallocHost((void **)&g->h_stage[i], TB_STAGE_BYTES));
+            TB_CUDA(cudaEventCreateWithFlags(&g->ev_stage[i], cudaEventDisableTiming));
+        }
+    const size_t chunks = (bytes + TB_STAGE_BYTES - 1) / TB_STAGE_BYTES;
+    for (size_t c = 0; c <= chunks; ++c)
+    {
+        if (c < chunks)
+        {
+            const size_t off = c * TB_STAGE_BYTES, len = std::min(TB_STAGE_BYTES, bytes - off);
+            TB_CUDA(cudaMemcpyAsync(g->h_stage[c & 1], (const char *)src_dev + off, len, cudaMemcpyDeviceToHost, st));
+            TB_CUDA(cudaEventRecord(g->ev_stage[c & 1], st));
+        }
+        if (c > 0)
+        {
+            const size_t off = (c - 1) * TB_STAGE_BYTES, len = std::min(TB_STAGE_BYTES, bytes - off);
+            TB_CUDA(cudaEventSynchronize(g->ev_stage[(c - 1) & 1]));
+            memcpy((char *)dst + off, g->h_stage[(c - 1) & 1], len);
+        }
+    }
+    return TB_OK;
+}
+
 extern "C" int tb_hecke_copy_sparse(tb_hecke *h, int64_t k, int32_t *data, int32_t *indices, int32_t *indptr)
 {
     if (!h || k < 0 || k >= h->C) return fail(TB_ERR_INVALID_ARGUMENT, "tb_hecke_copy_sparse: bad conductor index");
     cudaStream_t st = h->g->stream;
     const size_t nnz = (size_t)h->nnz[k];
-    if (nnz && data) TB_CUDA(cudaMemcpyAsync(data, h->d_data.ptr + h->nnzbase[k], nnz * sizeof(int), cudaMemcpyDefault, st));
-    if (nnz && indices) TB_CUDA(cudaMemcpyAsync(indices, h->d_indices.ptr + h->nnzbase[k], nnz * sizeof(int), cudaMemcpyDefault, st));
-    if (indptr) TB_CUDA(cudaMemcpyAsync(indptr, h->d_indptr.ptr + h->rowbase[k], ((size_t)h->rows[k] + 1) * sizeof(int), cudaMemcpyDefault, st));
+    if (nnz && data) if (int rc = copy_out(h->g, data, h->d_data.ptr + h->nnzbase[k], nnz * sizeof(int))) return rc;
+    if (nnz && indices) if (int rc = copy_out(h->g, indices, h->d_indices.ptr + h->nnzbase[k], nnz * sizeof(int))) return rc;
+    if (indptr) if (int rc = copy_out(h->g, indptr, h->d_indptr.ptr + h->rowbase[k], ((size_t)h->rows[k] + 1) * sizeof(int))) return rc;
     TB_CUDA(cudaStreamSynchronize(st));
     return TB_OK;
 }
@@ -915,11 +963,11 @@ extern "C" int tb_hecke_copy_dense(tb_hecke *h, int64_t k, int32_t *matrix)
     bool on_device = cudaPointerGetAttributes(&attr, matrix) == cudaSuccess &&
                      (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
     cudaGetLastError();
-    DevBuf<int> tmp;
+    PoolBuf<int> tmp;
     int *dst = matrix;
     if (!on_device)
     {
-        TB_CUDA(tmp.reserve(cells));
+        TB_CUDA(tmp.reserve(cells, st));
         dst = tmp.ptr;
     }
     TB_CUDA(cudaMemsetAsync(dst, 0, cells * sizeof(int), st));
@@ -930,7 +978,7 @@ extern "C" int tb_hecke_copy_dense(tb_hecke *h, int64_t k, int32_t *matrix)
         ++g_launches;
         TB_CUDA(cudaGetLastError());
     }
-    if (!on_device) TB_CUDA(cudaMemcpyAsync(matrix, dst, cells * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (!on_device) if (int rc = copy_out(h->g, matrix, dst, cells * sizeof(int))) { tmp.release(); return rc; }
     TB_CUDA(cudaStreamSynchronize(st));
     tmp.release();
     return TB_OK;
@@ -992,40 +1040,40 @@ extern "C" int tb_eigenvalues(tb_genus *g, uint64_t p, int precise, int64_t V, c
     std::vector<uint32_t> base;
     base_points_for(g, p, reps, base);
 
-    DevBuf<int> d_vecs, d_sel, d_out;
-    DevBuf<i64> d_cond;
-    auto cleanup = [&]() { d_vecs.release(); d_sel.release(); d_out.release(); d_cond.release(); };
-    TB_CUDA(d_vecs.reserve((size_t)V * N));
-    TB_CUDA(d_cond.reserve(V));
-    TB_CUDA(d_sel.reserve(V));
-    TB_CUDA(d_out.reserve(V));
+    // one launch sequence for all set-cover representatives: base points -> prep -> neighbors -> dot
+    const int R = (int)reps.size();
+    std::vector<int> rep_of_vec(V);
+    for (int64_t v = 0; v < V; ++v) rep_of_vec[v] = (int)rep_index[v];
+    PoolBuf<int> d_vecs, d_meta, d_out;     // d_meta = rep_list[R] | rep_of_vec[V]
+    PoolBuf<i64> d_cond;
+    auto cleanup = [&]() { d_vecs.release(); d_meta.release(); d_out.release(); d_cond.release(); };
+    TB_CUDA(d_vecs.reserve((size_t)V * N, g->stream));
+    TB_CUDA(d_cond.reserve(V, g->stream));
+    TB_CUDA(d_meta.reserve((size_t)R + V, g->stream));
+    TB_CUDA(d_out.reserve(V, g->stream));
     TB_CUDA(cudaMemcpyAsync(d_vecs.ptr, vecs, (size_t)V * N * sizeof(int), cudaMemcpyDefault, g->stream));
     TB_CUDA(cudaMemcpyAsync(d_cond.ptr, cond_mask, V * sizeof(i64), cudaMemcpyDefault, g->stream));
+    TB_CUDA(cudaMemcpyAsync(d_meta.ptr, reps.data(), R * sizeof(int), cudaMemcpyHostToDevice, g->stream));
+    TB_CUDA(cudaMemcpyAsync(d_meta.ptr + R, rep_of_vec.data(), V * sizeof(int), cudaMemcpyHostToDevice, g->stream));
     TB_CUDA(cudaMemsetAsync(d_out.ptr, 0, V * sizeof(int), g->stream));
-    TB_CUDA(g->d_W.reserve(P1));
-
-    std::vector<int> host_vecs_at_rep(V);
-    for (size_t i = 0; i < reps.size(); ++i)
-    {
-        const int n = reps[i];
-        std::vector<int> sel;
-        for (int64_t v = 0; v < V; ++v) if (rep_index[v] == n) sel.push_back((int)v);
-        g->rp_begin = -1;   // the staged rows below are not the Hecke shard's
-        if (int rc = stage_rows(g, &base[3 * i], n, 1)) { cleanup(); return rc; }
-        if (int rc = launch_neighbors<MODE_PACKED>(g, precise, n, 1, g->d_W.ptr, nullptr)) { cleanup(); return rc; }
-        TB_CUDA(cudaMemcpyAsync(g->h_err, g->d_err.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, g->stream));
-        TB_CUDA(cudaMemcpyAsync(d_sel.ptr, sel.data(), sel.size() * sizeof(int), cudaMemcpyHostToDevice, g->stream));
-        TB_CUDA(cudaStreamSynchronize(g->stream));
-        if (int rc = check_errors(g)) { cleanup(); return rc; }
-        eigen_dot_kernel<<<(P1 + 255) / 256, 256, 0, g->stream>>>(g->d_W.ptr, P1, g->K, N, d_vecs.ptr, d_cond.ptr,
-                                                                  d_sel.ptr, (int)sel.size(), d_out.ptr);
-        ++g_launches;
-        TB_CUDA(cudaGetLastError());
-        TB_CUDA(cudaStreamSynchronize(g->stream));
-    }
+    TB_CUDA(g->d_W.reserve((size_t)R * P1));
+    TB_CUDA(g->d_base.reserve(3 * (size_t)R));
+    TB_CUDA(g->d_rp.reserve(R));
+    g->rp_begin = -1;                                         // the staged rows below are not a Hecke shard's
+    TB_CUDA(cudaMemcpyAsync(g->d_base.ptr, base.data(), base.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, g->stream));
+    prep_reps_kernel<<<(R + 127) / 128, 128, 0, g->stream>>>(g->gc, g->ps.pc, g->d_base.ptr, 0, R, g->d_rp.ptr, d_meta.ptr);
+    ++g_launches;
+    if (int rc = launch_neighbors<MODE_PACKED>(g, precise, 0, R, g->d_W.ptr, nullptr, d_meta.ptr)) { cleanup(); return rc; }
+    eigen_dot_kernel<<<dim3((P1 + 255) / 256, R), 256, 0, g->stream>>>(g->d_W.ptr, P1, g->K, N, d_vecs.ptr, d_cond.ptr,
+                                                                       d_meta.ptr + R, (int)V, d_meta.ptr, d_out.ptr);
+    ++g_launches;
+    TB_CUDA(cudaGetLastError());
     std::vector<int> sums(V);
-    TB_CUDA(cudaMemcpy(sums.data(), d_out.ptr, V * sizeof(int), cudaMemcpyDeviceToHost));
+    TB_CUDA(cudaMemcpyAsync(g->h_err, g->d_err.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, g->stream));
+    TB_CUDA(cudaMemcpyAsync(sums.data(), d_out.ptr, V * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    TB_CUDA(cudaStreamSynchronize(g->stream));
     cleanup();
+    if (int rc = check_errors(g)) return rc;
     // host copy of the pivot coordinates for the final exact division (Genus.h:504-510)
     std::vector<int> pivot(V);
     cudaPointerAttributes attr;
