@@ -281,29 +281,50 @@ def main():
     d2h_bytes = sum(4 * (2 * nnz + rows + 1) for rows, _, nnz in shapes)
     last.close()
 
-    def step_e2e():
-        g.upload()                                   # genus table + per-prime inputs: host -> device
-        res = g.hecke_device(p)
+    # Two pinned result sets and a copy stream: the read-back of step i overlaps the compute of
+    # step i+1 (each step still moves its own inputs in and its own result out inside the timed region).
+    pinned = [pinned, [tuple(t.clone().pin_memory() for t in trio) for trio in pinned]]
+    copy_stream = torch.cuda.Stream(device=dev)
+    pending = [None, None]                               # (HeckeResult, event) per buffer set
+
+    def drain(slot):
+        if pending[slot] is not None:
+            res, ev = pending[slot]
+            ev.synchronize()
+            res.close()
+            pending[slot] = None
+
+    def step_e2e(i):
+        slot = i & 1
+        drain(slot)                                      # buffer set free again
+        g.upload()                                       # genus table + per-prime inputs: host -> device
+        res = g.hecke_device(p)                          # returns when the T_p is complete on the device
+        copy_stream.wait_stream(stream)
         for k in range(C):
-            d, i_, ptr = pinned[k]
+            d, i_, ptr = pinned[slot][k]
             rows, _, nnz = res.shape(k)
             assert nnz <= d.numel()
-            res.copy_sparse_to(k, d.data_ptr(), i_.data_ptr(), ptr.data_ptr())
-        res.close()
+            res.copy_sparse_to_async(k, d.data_ptr(), i_.data_ptr(), ptr.data_ptr(), copy_stream.cuda_stream)
+        ev = torch.cuda.Event()
+        ev.record(copy_stream)
+        pending[slot] = (res, ev)
 
-    step_e2e()
+    step_e2e(0)
+    drain(0)
     sync_all()
-    e_starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    e_stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    e_start = torch.cuda.Event(enable_timing=True)
+    e_stop = torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
+    e_start.record(stream)
     for i in range(args.steps):
-        e_starts[i].record(stream)
-        step_e2e()
-        e_stops[i].record(stream)
+        step_e2e(i)
+    drain(0)
+    drain(1)
+    e_stop.record(stream)
     sync_all()
     wall_e2e = time.perf_counter() - wall0
-    e_ms = sum(s.elapsed_time(e) for s, e in zip(e_starts, e_stops))
-    t = torch.tensor([max(e_ms, wall_e2e * 1e3 if world == 1 else e_ms)], dtype=torch.float64, device=dev)
+    e_ms = max(e_start.elapsed_time(e_stop), wall_e2e * 1e3)
+    t = torch.tensor([e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total_neighbors / (float(t.item()) * 1e-3)

@@ -110,6 +110,10 @@ int64_t tb_hecke_nnz(const tb_hecke *h, int64_t k);
 /* CSR triple in the reference's order (data, indices, indptr), Genus.h:662-671:
  * data[nnz], indices[nnz], indptr[rows+1]. */
 int tb_hecke_copy_sparse(tb_hecke *h, int64_t k, int32_t *data, int32_t *indices, int32_t *indptr);
+/* Same copy, enqueued on `cuda_stream` without synchronising (destinations must be device or
+ * pinned host memory): lets the caller overlap the read-back of one T_p with the next one. */
+int tb_hecke_copy_sparse_async(tb_hecke *h, int64_t k, int32_t *data, int32_t *indices, int32_t *indptr,
+                               void *cuda_stream);
 /* Row-major rows x dim block, Genus.h:811-846. */
 int tb_hecke_copy_dense(tb_hecke *h, int64_t k, int32_t *matrix);
 void tb_hecke_destroy(tb_hecke *h);

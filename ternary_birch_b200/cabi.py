@@ -63,6 +63,7 @@ def lib() -> ctypes.CDLL:
         getattr(L, name).argtypes = [vp, i64]
         getattr(L, name).restype = i64
     L.tb_hecke_copy_sparse.argtypes = [vp, i64, vp, vp, vp]
+    L.tb_hecke_copy_sparse_async.argtypes = [vp, i64, vp, vp, vp, vp]
     L.tb_hecke_copy_dense.argtypes = [vp, i64, vp]
     L.tb_hecke_destroy.argtypes = [vp]
     L.tb_hecke_destroy.restype = None
@@ -92,6 +93,7 @@ EXPORTS = [
     "tb_genus_num_conductors", "tb_genus_conductor", "tb_genus_dim",
     "tb_hecke_compute", "tb_hecke_compute_rows", "tb_hecke_num_conductors", "tb_hecke_conductor",
     "tb_hecke_dim", "tb_hecke_rows", "tb_hecke_row_begin", "tb_hecke_nnz", "tb_hecke_copy_sparse",
+    "tb_hecke_copy_sparse_async",
     "tb_hecke_copy_dense", "tb_hecke_destroy", "tb_eigenvalues", "tb_isoseq_open", "tb_isoseq_done",
     "tb_isoseq_next", "tb_isoseq_read", "tb_isoseq_close", "tb_neighbor_records", "tb_int_peak",
     "tb_quad_form", "tb_genus_enumerate", "tb_table_desc", "tb_table_destroy",

@@ -951,6 +951,18 @@ extern "C" int tb_hecke_copy_sparse(tb_hecke *h, int64_t k, int32_t *data, int32
     return TB_OK;
 }
 
+extern "C" int tb_hecke_copy_sparse_async(tb_hecke *h, int64_t k, int32_t *data, int32_t *indices, int32_t *indptr,
+                                          void *cuda_stream)
+{
+    if (!h || k < 0 || k >= h->C) return fail(TB_ERR_INVALID_ARGUMENT, "tb_hecke_copy_sparse_async: bad conductor index");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t nnz = (size_t)h->nnz[k];
+    if (nnz && data) TB_CUDA(cudaMemcpyAsync(data, h->d_data.ptr + h->nnzbase[k], nnz * sizeof(int), cudaMemcpyDefault, st));
+    if (nnz && indices) TB_CUDA(cudaMemcpyAsync(indices, h->d_indices.ptr + h->nnzbase[k], nnz * sizeof(int), cudaMemcpyDefault, st));
+    if (indptr) TB_CUDA(cudaMemcpyAsync(indptr, h->d_indptr.ptr + h->rowbase[k], ((size_t)h->rows[k] + 1) * sizeof(int), cudaMemcpyDefault, st));
+    return TB_OK;
+}
+
 extern "C" int tb_hecke_copy_dense(tb_hecke *h, int64_t k, int32_t *matrix)
 {
     if (!h || k < 0 || k >= h->C) return fail(TB_ERR_INVALID_ARGUMENT, "tb_hecke_copy_dense: bad conductor index");

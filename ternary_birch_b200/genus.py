@@ -287,6 +287,11 @@ class HeckeResult:
         cabi.check(cabi.lib().tb_hecke_copy_sparse(self._h, k, ctypes.c_void_p(data_ptr),
                                                    ctypes.c_void_p(indices_ptr), ctypes.c_void_p(indptr_ptr)))
 
+    def copy_sparse_to_async(self, k, data_ptr: int, indices_ptr: int, indptr_ptr: int, cuda_stream: int) -> None:
+        """Enqueue the copy on `cuda_stream` (device or pinned destinations) without synchronising."""
+        cabi.check(cabi.lib().tb_hecke_copy_sparse_async(self._h, k, ctypes.c_void_p(data_ptr), ctypes.c_void_p(indices_ptr),
+                                                         ctypes.c_void_p(indptr_ptr), ctypes.c_void_p(cuda_stream)))
+
     def sparse(self, k):
         rows, _, nnz = self.shape(k)
         data = np.empty(nnz, dtype=np.int32)

@@ -67,7 +67,7 @@ def test_even_level(genus, hecke_small):
     ("85085", 2, False), ("85085", 2, True), ("85085", 3, False), ("85085", 19, True),
     ("85085", 101, False), ("85085", 101, True), ("85085", 997, False),
     ("1062347", 2, False), ("1062347", 3, True), ("1062347", 101, False), ("1062347", 101, True),
-    ("1009091", 2, False), ("1009091", 107, False),
+    ("1009091", 2, False), ("1009091", 107, False), ("1009091", 1009, False),
 ])
 def test_hecke_vs_oracle_and_golden(genus, port_oracle, hecke_digests, name, p, precise):
     """Configs 2-4 (sampled primes): every CSR array equals the oracle's, and its digest equals
@@ -253,3 +253,29 @@ def test_size_independent_properties_full_size(genus):
     aut = g.table.num_auts.astype(np.int64)
     TA = T.multiply(aut[None, :]).tocsr()           # (T A)[n][r] = T[n][r] * aut[r]
     assert (TA != TA.T.tocsr()).nnz == 0            # T A is symmetric
+
+
+def test_bench_workload_properties(genus):
+    """The bench workload itself (C4: N = 10316, T_9973, int64 and precise): conductor-1 rows sum
+    to p + 1, T A is symmetric for A = diag(|Aut|), both integer modes agree entry for entry, and
+    the row blocks of a 3-way representative shard concatenate to the full matrix."""
+    from scipy.sparse import csr_matrix
+    p = 9973
+    g = genus("1009091", False)
+    N = g.table.N
+    full = g.hecke_matrix_sparse(p)
+    data, indices, indptr = full[1]
+    assert (np.add.reduceat(data.astype(np.int64), indptr[:-1]) == p + 1).all()
+    T = csr_matrix((data.astype(np.int64), indices, indptr), shape=(N, N))
+    TA = T.multiply(g.table.num_auts.astype(np.int64)[None, :]).tocsr()
+    assert (TA != TA.T.tocsr()).nnz == 0
+    precise = genus("1009091", True).hecke_matrix_sparse(p)
+    for cond in full:
+        for a, b in zip(full[cond], precise[cond]):
+            assert np.array_equal(a, b), cond
+    from ternary_birch_b200 import shard
+    parts = [g.hecke_matrix_sparse(p, a, b) for a, b in shard.row_shards(N, 3)]
+    whole = shard.concat_row_shards(parts)
+    for cond in (1, 97, 1009091):
+        for a, b in zip(whole[cond], full[cond]):
+            assert np.array_equal(a, b), cond
