@@ -400,6 +400,16 @@ int tbo_reduced_neighbor(const int64_t q[6], const int64_t vec[3], uint64_t p, i
     return err;
 }
 
+/* Loop trips QuadForm::reduce takes on the neighbor along `vec` (profiling aid). */
+int tbo_reduce_iterations(const int64_t q[6], const int64_t vec[3], uint64_t p)
+{
+    int err = TBO_OK;
+    form_i128 cur = load_form_i128(q), nq;
+    iso_i128 s;
+    if (build_neighbor_i128(&cur, vec, p, &nq, &s)) return -1;
+    return reduce_i128(&nq, &s, &err);
+}
+
 void tbo_reduce(int64_t q[6], int64_t s[9], int precise)
 {
     int err = TBO_OK;

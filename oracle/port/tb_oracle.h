@@ -72,6 +72,9 @@ void tbo_isotropic_vector(const int64_t q[6], const int64_t base[3], uint64_t p,
 int tbo_reduced_neighbor(const int64_t q[6], const int64_t vec[3], uint64_t p, int precise,
                          int64_t out_q[6], int64_t out_s[9]);
 
+/* Loop trips of QuadForm::reduce on the neighbor along `vec` (profiling aid). */
+int tbo_reduce_iterations(const int64_t q[6], const int64_t vec[3], uint64_t p);
+
 /* QuadForm::reduce alone, on int64 input (s is updated in place). */
 void tbo_reduce(int64_t q[6], int64_t s[9], int precise);
 

@@ -54,3 +54,42 @@ def test_enumeration_vs_reference_binary(level, seed):
     assert got.N == want.N
     for field in ("primes", "conductors", "dims", "q", "parent", "p", "num_auts", "scalar", "s", "sinv", "lut"):
         assert np.array_equal(getattr(got, field), getattr(want, field)), field
+
+
+def test_randomised_levels_end_to_end_vs_reference_binary():
+    """A deterministic sweep over further levels (odd / even, 1-4 prime divisors, varying seeds):
+    build the genus here, then compare T_p (both integer modes), an isometry sequence and the genus
+    table itself with the unmodified reference run on the same box."""
+    from oracle.pyoracle import RefBinary
+    if not RefBinary.available():
+        pytest.skip("oracle/_ref not present")
+    from ternary_birch_b200 import Genus, IsometrySequence, build_genus_table
+    rng = np.random.default_rng(20261019)
+    pool = [2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47]
+    done = 0
+    while done < 6:
+        k = int(rng.integers(1, 5))
+        ps = sorted(int(x) for x in rng.choice(pool, size=k, replace=False))
+        level = int(np.prod(ps))
+        if level > 40000:
+            continue
+        seed = int(rng.integers(1, 1000))
+        ref = RefBinary(level, seed)
+        want = ref.genus()
+        got = build_genus_table(level, seed=seed)
+        for field in ("q", "s", "sinv", "scalar", "lut", "dims", "num_auts"):
+            assert np.array_equal(getattr(got, field), getattr(want, field)), (level, seed, field)
+        good = [p for p in (2, 3, 5, 7, 11, 13) if level % p][:3]
+        for precise in (False, True):
+            g = Genus(got, precise=precise)
+            for p in good:
+                mine = g.hecke_matrix_sparse(p)
+                for m in ref.hecke(p, precise, True):
+                    d, i, ptr = mine[m["conductor"]]
+                    assert np.array_equal(d, m["data"]) and np.array_equal(i, m["indices"]) and np.array_equal(ptr, m["indptr"]), (level, seed, p, precise)
+            seq = IsometrySequence(g, good[0])
+            rec = seq.read(got.N * (good[0] + 1))
+            assert np.array_equal(rec, ref.isometry_sequence(good[0], precise)), (level, seed, precise)
+            seq.close()
+            g.close()
+        done += 1
