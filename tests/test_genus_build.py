@@ -93,3 +93,26 @@ def test_randomised_levels_end_to_end_vs_reference_binary():
             seq.close()
             g.close()
         done += 1
+
+
+@pytest.mark.parametrize("level", [2, 3, 5, 7, 13, 37])
+def test_class_number_one_and_two(level):
+    """Smallest genera (one or two classes; level 2 makes p = 2 a bad prime)."""
+    from ternary_birch_b200 import BirchGenus
+    g = BirchGenus(level, seed=1)
+    n = g.dimensions()[1]
+    assert n == (2 if level == 37 else 1)
+    for p in (2, 3, 5, 101):
+        if level % p == 0:
+            with pytest.raises(Exception):
+                g.hecke_matrix(p, 1, precise=False)
+            continue
+        for precise in (False, True):
+            g.hecke = {}
+            T = g.hecke_matrix(p, 1, sparse=False, precise=precise)
+            assert T.shape == (n, n) and (T.sum(axis=1) == p + 1).all()
+            g.hecke = {}
+            S = g.hecke_matrix(p, 1, sparse=True, precise=precise)
+            assert (np.asarray(S.todense()) == T).all()
+    recs = list(g.isometry_sequence(3 if level != 3 else 5))
+    assert len(recs) == n * ((3 if level != 3 else 5) + 1)
