@@ -174,6 +174,28 @@ def run_reference_arm(args):
     return 0
 
 
+def bind_to_gpu_numa_node(torch, local_rank: int):
+    """Best effort: run this rank (and so its pinned-memory allocations, first touch) on the CPUs of
+    the NUMA node its GPU hangs off, so the end-to-end copies of 8 ranks do not cross sockets."""
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # ---------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------
@@ -202,6 +224,7 @@ def main():
         sys.exit("bench.py: no CUDA device; this path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(torch, local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -394,7 +417,7 @@ def main():
                                 sharding="one T_p per rank per step (prime axis), no data-path collective"),
                     roofline=roofline, cpu_baseline=cpu,
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes),
-                    gpu_launches=int(launches_timed), clocks=clocks, T_p_wall_ms=total_ms / args.steps,
+                    gpu_launches=int(launches_timed), clocks=clocks, numa_node=numa_node, T_p_wall_ms=total_ms / args.steps,
                     final_gather_ms=gather_ms)
         print(json.dumps(line), flush=True)
     g.close()

@@ -22,6 +22,9 @@ def pytest_sessionstart(session):
     # (the C port always; oracle/_ref only where /root/reference exists)
     from oracle import pyoracle
     pyoracle.build()
+    # the product library: (re)built in-tree when missing or stale (nvcc cross-compiles without a GPU)
+    import __graft_entry__ as ge
+    ge.build()
 
 
 def has_gpu() -> bool:
