@@ -205,7 +205,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precise", action="store_true", help="checked 128-bit mode instead of int64")
+    ap.add_argument("--precise", action="store_true", help="the reference's arbitrary-precision mode (Genus<Z>) instead of int64")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -395,7 +395,7 @@ def main():
             traffic = json.load(open(tf)).get("dram_bytes_per_launch")
         roofline = dict(bound="int32-issue", achieved=achieved, peak=measured_peak, unit="Tint32op/s",
                         frac=achieved / measured_peak, traffic=traffic,
-                        kernel="neighbors_kernel<W64,PACKED>", kernel_ms=kms, rows_kernels_ms=rms,
+                        kernel="neighbors_kernel<%s,PACKED>" % {"int64-wrap": "W64", "int64-bounded": "X64", "int128-bounded": "U128", "int128-checked": "C128"}[g.last_int_mode()], kernel_ms=kms, rows_kernels_ms=rms,
                         int32_ops_per_neighbor=w32, peak_source="tb_int_peak microbenchmark, measured in this run "
                         "(IMAD/IADD3+LOP3 chains on all SMs)", peak_detail=peak,
                         hbm=dict(achieved=hbm_achieved, peak=hbm_peak, unit="GB/s", frac=hbm_achieved / hbm_peak,
@@ -410,7 +410,7 @@ def main():
                               f"{len(primes)} primes {primes[0]}..{primes[-1]}, one process per prime; {s:.1f} s wall")
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="int128-checked" if args.precise else "int64", data="synthetic",
+                    dtype=g.last_int_mode() if args.precise else "int64", data="synthetic",
                     config=dict(workload=workload_name(p), neighbors_per_step_per_gpu=neighbors_per_step,
                                 l2="flushed between timed steps (256 MB write); the 412 MB packed-word stream "
                                    "exceeds L2, the 3 MB genus table is L2-resident by design",

@@ -75,6 +75,11 @@ uint64_t tb_launch_count(void);
 /* Device time in ms of the last neighbor-kernel launch sequence of `g`
  * (CUDA events on g's stream), and the number of neighbors it covered. */
 int tb_last_kernel_time(tb_genus *g, float *ms_neighbors, float *ms_rows, int64_t *neighbors);
+/* Integer mode of g's last neighbor-kernel launch (diagnostic; results never depend on it):
+ * 0 = wrap-around int64 (precise = 0, Genus<Z64>); precise = 1 (Genus<Z>) runs as
+ * 1 = 64-bit under host-proven magnitude bounds, 2 = unchecked 128-bit under proven bounds,
+ * 3 = overflow-checked 128-bit.  -1 before the first launch. */
+int tb_last_int_mode(const tb_genus *g);
 
 /* ---- genus table ------------------------------------------------------ */
 /* Replaces the state built by Genus<R>::Genus (Genus.h:37-246) and copied by the

@@ -44,6 +44,7 @@ def lib() -> ctypes.CDLL:
     L.tb_last_error.restype = ctypes.c_char_p
     L.tb_launch_count.restype = u64
     L.tb_last_kernel_time.argtypes = [vp, vp, vp, vp]
+    L.tb_last_int_mode.argtypes = [vp]
     L.tb_genus_create.argtypes = [ctypes.POINTER(GenusDesc), ctypes.POINTER(vp)]
     L.tb_genus_destroy.argtypes = [vp]
     L.tb_genus_destroy.restype = None
@@ -88,7 +89,7 @@ def lib() -> ctypes.CDLL:
 
 
 EXPORTS = [
-    "tb_abi_version", "tb_last_error", "tb_launch_count", "tb_last_kernel_time",
+    "tb_abi_version", "tb_last_error", "tb_launch_count", "tb_last_kernel_time", "tb_last_int_mode",
     "tb_genus_create", "tb_genus_destroy", "tb_genus_set_stream", "tb_genus_upload", "tb_genus_size",
     "tb_genus_num_conductors", "tb_genus_conductor", "tb_genus_dim",
     "tb_hecke_compute", "tb_hecke_compute_rows", "tb_hecke_num_conductors", "tb_hecke_conductor",

@@ -101,13 +101,19 @@ __device__ __forceinline__ void udivmod128(u64 hi, u64 lo, const InvDiv &iv, u64
 }
 
 // ---------------------------------------------------------------------------
-// W64: wrap-around int64.
+// I64T<TAG>: int64 with wrap-around ring operations.  W64 = I64T<0> is the reference's
+// Genus<Z64>.  X64 = I64T<1> is the same machine arithmetic used for precise = 1 launches
+// whose every intermediate the host has PROVEN to stay inside int64 (precise_bounds_ok64),
+// except the one term of build_neighbor that is carried in 128 bits (wide_muladd_div) and
+// the rare spinor-norm branches, which widen to U128.
 // ---------------------------------------------------------------------------
-struct W64 {
+template <int TAG>
+struct I64T {
+    typedef I64T W64;
     i64 v;
 
-    __device__ __forceinline__ W64() {}
-    __device__ __forceinline__ W64(i64 x) : v(x) {}
+    __device__ __forceinline__ I64T() {}
+    __device__ __forceinline__ I64T(i64 x) : v(x) {}
     __device__ __forceinline__ static W64 from_i64(i64 x) { return W64(x); }
 
     __device__ __forceinline__ i64 low64() const { return v; }
@@ -138,27 +144,32 @@ struct W64 {
     // times 2 / times 4 (ring ops)
     __device__ __forceinline__ W64 twice() const { return W64((i64)((u64)v << 1)); }
 };
+typedef I64T<0> W64;
+typedef I64T<1> X64;
 
 // C truncating x % d and x / d by an invariant positive divisor.
-__device__ __forceinline__ W64 trunc_rem(W64 x, const InvDiv &iv)
+template <int TAG>
+__device__ __forceinline__ I64T<TAG> trunc_rem(I64T<TAG> x, const InvDiv &iv)
 {
     u64 r;
     udivmod(x.umag(), iv, r);
-    return x.v < 0 ? W64(-(i64)r) : W64((i64)r);
+    return x.v < 0 ? I64T<TAG>(-(i64)r) : I64T<TAG>((i64)r);
 }
-__device__ __forceinline__ W64 trunc_div(W64 x, const InvDiv &iv)
+template <int TAG>
+__device__ __forceinline__ I64T<TAG> trunc_div(I64T<TAG> x, const InvDiv &iv)
 {
     u64 r;
     u64 q = udivmod(x.umag(), iv, r);
-    return x.v < 0 ? W64((i64)(0ull - q)) : W64((i64)q);
+    return x.v < 0 ? I64T<TAG>((i64)(0ull - q)) : I64T<TAG>((i64)q);
 }
 // x is a multiple of d?  If so replace x by x / d.
-__device__ __forceinline__ bool strip_factor(W64 &x, const InvDiv &iv)
+template <int TAG>
+__device__ __forceinline__ bool strip_factor(I64T<TAG> &x, const InvDiv &iv)
 {
     u64 r;
     u64 q = udivmod(x.umag(), iv, r);
     if (r != 0) return false;
-    x = x.v < 0 ? W64((i64)(0ull - q)) : W64((i64)q);
+    x = x.v < 0 ? I64T<TAG>((i64)(0ull - q)) : I64T<TAG>((i64)q);
     return true;
 }
 
@@ -168,7 +179,8 @@ __device__ __forceinline__ bool strip_factor(W64 &x, const InvDiv &iv)
 // floor(num/den); the general branch keeps the reference's exact behaviour on
 // wrapped garbage, except that den == 0 (a SIGFPE in the reference) raises the
 // overflow flag.
-__device__ __forceinline__ W64 ref_quotient(W64 num, W64 den)
+template <int TAG>
+__device__ __forceinline__ I64T<TAG> ref_quotient(I64T<TAG> num, I64T<TAG> den)
 {
     const i64 n = num.v, d = den.v;
     if (n >= 0 && d > 0 && n < (1ll << 50))
@@ -178,20 +190,20 @@ __device__ __forceinline__ W64 ref_quotient(W64 num, W64 den)
         i64 r = n - q * d;
         if (r < 0) { q -= 1; r += d; }
         if (r >= d) { q += 1; }
-        return W64(q);
+        return I64T<TAG>(q);
     }
-    if (n < d) return W64(0);
-    W64 D(d);
-    if (num < W64(5) * D)
+    if (n < d) return I64T<TAG>(0);
+    I64T<TAG> D(d);
+    if (num < I64T<TAG>(5) * D)
     {
-        if (num < W64(3) * D) return (num < W64(2) * D) ? W64(1) : W64(2);
-        return (num < W64(4) * D) ? W64(3) : W64(4);
+        if (num < I64T<TAG>(3) * D) return (num < I64T<TAG>(2) * D) ? I64T<TAG>(1) : I64T<TAG>(2);
+        return (num < I64T<TAG>(4) * D) ? I64T<TAG>(3) : I64T<TAG>(4);
     }
-    if (num < W64(7) * D) return (num < W64(6) * D) ? W64(5) : W64(6);
-    if (num < W64(8) * D) return W64(7);
-    if (d == 0) { raise_overflow(); return W64(0); }
+    if (num < I64T<TAG>(7) * D) return (num < I64T<TAG>(6) * D) ? I64T<TAG>(5) : I64T<TAG>(6);
+    if (num < I64T<TAG>(8) * D) return I64T<TAG>(7);
+    if (d == 0) { raise_overflow(); return I64T<TAG>(0); }
     if (d == -1) return -num;          // INT64_MIN / -1 traps on x86; wrap instead
-    return W64(n / d);
+    return I64T<TAG>(n / d);
 }
 
 // ---------------------------------------------------------------------------
@@ -380,5 +392,32 @@ __device__ __forceinline__ I128<CHK> ref_quotient(I128<CHK> num, I128<CHK> den)
 
 typedef I128<true> C128;
 typedef I128<false> U128;
+
+// trunc((acc + x * y) / d): the two terms of build_neighbor (NeighborManager.h:325-341) whose
+// numerators are the largest values the build forms.  X64 carries the numerator in 128 bits;
+// the quotient is proven to fit int64, so the high limb is below d and one 2-by-1 step suffices.
+template <class Z>
+__device__ __forceinline__ Z muladd_div(Z acc, Z x, Z y, const InvDiv &iv)
+{
+    return trunc_div(acc + x * y, iv);
+}
+template <>
+__device__ __forceinline__ X64 muladd_div<X64>(X64 acc, X64 x, X64 y, const InvDiv &iv)
+{
+    const u64 lo = (u64)x.v * (u64)y.v;
+    const i64 hi = __mul64hi(x.v, y.v);
+    u64 slo = lo + (u64)acc.v;
+    u64 shi = (u64)hi + (u64)(acc.v >> 63) + (slo < lo ? 1ull : 0ull);
+    const bool neg = (i64)shi < 0;
+    if (neg)
+    {
+        slo = 0ull - slo;
+        shi = ~shi + (slo == 0 ? 1ull : 0ull);
+    }
+    const u64 u1 = iv.s ? ((shi << iv.s) | (slo >> (64 - iv.s))) : shi;
+    u64 r;
+    const u64 q = div2by1(u1, slo << iv.s, iv.dn, iv.v, r);
+    return X64(neg ? (i64)(0ull - q) : (i64)q);
+}
 
 }  // namespace tb

@@ -178,6 +178,7 @@ struct NbrLaunch {
 // two-limb kernels need ~3x the live state
 template <class Z> struct NbrBlocks { static const int value = 3; };
 template <> struct NbrBlocks<W64> { static const int value = TB_NBR_MINBLOCKS; };
+template <> struct NbrBlocks<X64> { static const int value = TB_NBR_MINBLOCKS; };
 
 template <class Z, int MODE>
 __global__ void __launch_bounds__(TB_NBR_THREADS, NbrBlocks<Z>::value)

@@ -268,6 +268,11 @@ template <class Z>
 struct CheckDisc { static const bool value = false; };
 template <>
 struct CheckDisc<W64> { static const bool value = true; };
+// X64: 64-bit arithmetic under host-proven bounds (exact, so no discriminant check)
+template <class Z>
+struct IsExact64 { static const bool value = false; };
+template <>
+struct IsExact64<X64> { static const bool value = true; };
 
 template <class Z>
 __device__ __forceinline__ Z form_disc(const Form<Z> &q)
@@ -343,7 +348,8 @@ __device__ __forceinline__ bool build_neighbor(const Form<Z> &q, u32 vx, u32 vy,
     const Z ginv = Z((i64)fp_inv((u32)gmodp.low64(), pc));   // 303
 
     Z s1 = trunc_rem((-hh) * ginv, pc.dp);                   // 309-312
-    Z s2 = trunc_rem((-aa) * ginv, pc.dpp);
+    // X64: reduce aa first so the product stays below p^3 (same truncated remainder)
+    Z s2 = IsExact64<Z>::value ? trunc_rem(trunc_rem(-aa, pc.dpp) * ginv, pc.dpp) : trunc_rem((-aa) * ginv, pc.dpp);
     if (s1 < Z(-half)) s1 += p;
     if (s2 < Z(-(i64)(pc.pp >> 1))) s2 += pp;
 
@@ -355,15 +361,13 @@ __device__ __forceinline__ bool build_neighbor(const Form<Z> &q, u32 vx, u32 vy,
 
     s.c1_add_c3(s2);                                         // 325-329
     Z temp2 = cc * s2;
-    aa += s2 * (gg + temp2);
+    aa = muladd_div(aa, s2, gg + temp2, pc.dpp);             // aa += s2 * (gg + temp2); ... aa /= pp  (341)
     gg += temp2.twice();
-    hh += s2 * ff;
+    hh = muladd_div(hh, s2, ff, pc.dp);                      // hh += s2 * ff; ... hh /= p
 
     s.scale_p(p, pp);                                        // 337-341
-    aa = trunc_div(aa, pc.dpp);
     cc *= pp;
     ff *= p;
-    hh = trunc_div(hh, pc.dp);
 
     out.a = aa; out.b = bb; out.c = cc; out.f = ff; out.g = gg; out.h = hh;
 
@@ -619,7 +623,8 @@ __device__ __forceinline__ double dshear_t(double a, double h, double den, doubl
 
 // 2^50 magnitude test on an int64
 __device__ __forceinline__ bool small50(i64 v) { return (u64)(v + (1ll << 50)) < (1ull << 51); }
-__device__ __forceinline__ bool fits50(W64 x) { return small50(x.v); }
+template <int TAG>
+__device__ __forceinline__ bool fits50(I64T<TAG> x) { return small50(x.v); }
 template <bool CHK>
 __device__ __forceinline__ bool fits50(I128<CHK> x) { return x.fits_i64() && small50((i64)x.lo); }
 
@@ -883,7 +888,8 @@ __device__ __forceinline__ u32 parities_u64(u64 y, const GenusCtx &gc)
     }
     return val;
 }
-__device__ __forceinline__ u32 prime_parities(W64 x, const GenusCtx &gc)
+template <int TAG>
+__device__ __forceinline__ u32 prime_parities(I64T<TAG> x, const GenusCtx &gc)
 {
     if (x.is_zero()) { raise_overflow(); return 0; }   // the reference's loop would not terminate
     return parities_u64(x.umag(), gc);
@@ -923,6 +929,22 @@ __device__ __forceinline__ u32 spinor_norm(const Form<Z> &q, const Iso<Z> &s, Z 
         return prime_parities(abhm33 - abh * scalar, gc) ^ prime_parities(q.a.twice(), gc) ^ twist;
 
     return prime_parities(abh * scalar, gc);
+}
+
+// X64: the first case is exact in 64 bits (|tr + scalar| < 2^63 by the host's bounds); the
+// later cases multiply form minors into the isometry, so they run in U128.  They are rare.
+template <>
+__device__ __forceinline__ u32 spinor_norm<X64>(const Form<X64> &q, const Iso<X64> &s, X64 scalar, const GenusCtx &gc)
+{
+    X64 tr = s.a11 + s.a22 + s.a33;
+    if (tr != -scalar) return prime_parities(tr + scalar, gc);
+    Form<U128> qw;
+    Iso<U128> sw;
+    qw.a = U128(q.a.v); qw.b = U128(q.b.v); qw.c = U128(q.c.v); qw.f = U128(q.f.v); qw.g = U128(q.g.v); qw.h = U128(q.h.v);
+    sw.a11 = U128(s.a11.v); sw.a12 = U128(s.a12.v); sw.a13 = U128(s.a13.v);
+    sw.a21 = U128(s.a21.v); sw.a22 = U128(s.a22.v); sw.a23 = U128(s.a23.v);
+    sw.a31 = U128(s.a31.v); sw.a32 = U128(s.a32.v); sw.a33 = U128(s.a33.v);
+    return spinor_norm<U128>(qw, sw, U128(scalar.v), gc);
 }
 
 template <class Z>
@@ -967,6 +989,7 @@ enum NeighborStatus { NBR_OK = 0, NBR_OVERFLOW = 1, NBR_NOT_FOUND = 2 };
 
 template <class Z> struct IsWide { static const bool value = true; };
 template <> struct IsWide<W64> { static const bool value = false; };
+template <> struct IsWide<X64> { static const bool value = false; };
 
 template <class Z>
 struct Neighbor {

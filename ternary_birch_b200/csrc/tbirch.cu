@@ -248,6 +248,8 @@ struct tb_genus {
     DevBuf<u64> d_lookback;     // [2^K][rows] look-back words + ticket (fused row kernel)
     bool allow_fused = true;
     bool force_checked = false;   // TBIRCH_FORCE_CHECKED: always run the checked C128 kernel in precise mode
+    int last_int_mode = -1;       // tb_last_int_mode
+    bool force_wide = false;      // TBIRCH_FORCE_WIDE: never run precise launches in the bounded 64-bit mode
     size_t device_bytes = 0;
     // per-shard row bookkeeping of the last Hecke call (reused while the shard is unchanged)
     int shard_begin = -1, shard_end = -1;
@@ -445,6 +447,7 @@ extern "C" int tb_genus_create(const tb_genus_desc *d, tb_genus **out)
     if (int rc = upload_table(g.get(), d)) return rc;
     g->allow_fused = getenv("TBIRCH_TWO_PASS_ROWS") == nullptr;   // debugging / A-B switches
     g->force_checked = getenv("TBIRCH_FORCE_CHECKED") != nullptr;
+    g->force_wide = getenv("TBIRCH_FORCE_WIDE") != nullptr;
     TB_CUDA(g->d_err.reserve(2));
     TB_CUDA(g->d_tab.reserve(3 * (size_t)C));
     TB_CUDA(g->d_nnz.reserve(2 * (size_t)C));
@@ -516,6 +519,8 @@ extern "C" int tb_last_kernel_time(tb_genus *g, float *ms_nbr, float *ms_rows, i
     if (neighbors) *neighbors = g->last_neighbors;
     return TB_OK;
 }
+
+extern "C" int tb_last_int_mode(const tb_genus *g) { return g ? g->last_int_mode : -1; }
 
 // ---------------------------------------------------------------------------
 // per-prime setup
@@ -666,6 +671,23 @@ static bool precise_bounds_ok(const tb_genus *g)
     return build < 120 && comp < 120 && denom < 120 && spin_comp < 120 && spin_self < 120;
 }
 
+// May a precise launch run in 64-bit machine arithmetic (X64)?  On top of the U128 conditions:
+//   build_neighbor   ring operations are exact modulo 2^64, so only the values that feed a
+//                    division, a comparison or the output must truly fit: all are below
+//                    4 A (p + 4)^2 once the two large numerators go through muladd_div and
+//                    s2 is taken from aa mod p^2 (needs p^3 < 2^63)
+//   reduce           FP64 loop, or the integer loop whose values stay below 8x its input
+//   trace / compose  composed isometry and denominator below 2^61 (narrow_trace)
+//   Spinor::norm     first case in 64 bits, the others widen to U128 on the device
+static bool precise_bounds_ok64(const tb_genus *g)
+{
+    const PrimeCtx &pc = g->ps.pc;
+    if (!precise_bounds_ok(g) || !pc.narrow_trace || g->force_wide) return false;
+    const double lp = log2((double)pc.p + 4.0);
+    const double iso = 1 + lp + 0.5 * (g->log2_coef - log2(g->lambda_min));
+    return lp < 20 && g->log2_coef + 2 * lp < 58 && iso < 60;
+}
+
 template <int MODE>
 static int launch_neighbors(tb_genus *g, int precise, int rep_begin, int rows, u32 *W, i64 *records,
                             const int *rep_list = nullptr)
@@ -685,7 +707,10 @@ static int launch_neighbors(tb_genus *g, int precise, int rep_begin, int rows, u
     const u64 blocks = (L.total + TB_NBR_THREADS - 1) / TB_NBR_THREADS;
     if (blocks > 0x7fffffffull) return fail(TB_ERR_RUNTIME, "libtbirch: launch too large");
     TB_CUDA(cudaMemsetAsync(g->d_err.ptr, 0xff, 2 * sizeof(u64), g->stream));
-    if (precise && precise_bounds_ok(g) && !g->force_checked)
+    g->last_int_mode = !precise ? 0 : g->force_checked ? 3 : precise_bounds_ok64(g) ? 1 : precise_bounds_ok(g) ? 2 : 3;
+    if (g->last_int_mode == 1)
+        neighbors_kernel<X64, MODE><<<(unsigned)blocks, TB_NBR_THREADS, 0, g->stream>>>(g->gc, g->ps.pc, L);
+    else if (g->last_int_mode == 2)
         neighbors_kernel<U128, MODE><<<(unsigned)blocks, TB_NBR_THREADS, 0, g->stream>>>(g->gc, g->ps.pc, L);
     else if (precise)
         neighbors_kernel<C128, MODE><<<(unsigned)blocks, TB_NBR_THREADS, 0, g->stream>>>(g->gc, g->ps.pc, L);

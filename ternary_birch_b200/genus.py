@@ -260,6 +260,12 @@ class Genus:
         cabi.check(cabi.lib().tb_last_kernel_time(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)))
         return a.value, b.value, n.value
 
+    INT_MODES = {-1: "none", 0: "int64-wrap", 1: "int64-bounded", 2: "int128-bounded", 3: "int128-checked"}
+
+    def last_int_mode(self) -> str:
+        """Integer mode the last neighbor kernel ran in (diagnostic)."""
+        return self.INT_MODES[int(cabi.lib().tb_last_int_mode(self._h))]
+
 
 class HeckeResult:
     """All 2^K matrices of one T_p, resident on the device until copied."""

@@ -279,3 +279,47 @@ def test_bench_workload_properties(genus):
     for cond in (1, 97, 1009091):
         for a, b in zip(whole[cond], full[cond]):
             assert np.array_equal(a, b), cond
+
+
+@pytest.mark.parametrize("name,p", [("85085", 101), ("1009091", 1009), ("1062347", 4099), ("11", 7)])
+def test_precise_kernel_variants_agree(tables, port_oracle, monkeypatch, name, p):
+    """precise = 1 runs in one of three integer modes chosen from magnitude bounds the host proves
+    per prime: 64-bit (bounded), unchecked 128-bit (bounded), overflow-checked 128-bit.  All three
+    must give the reference's records, isometries and matrices bit for bit."""
+    from ternary_birch_b200 import Genus, IsometrySequence
+    t = tables(name)
+    rows = min(t.N, 24)
+    small = t.N * (p + 1) <= 200000
+    got = {}
+    for env, want_mode in ((None, "int64-bounded"), ("TBIRCH_FORCE_WIDE", "int128-bounded"),
+                           ("TBIRCH_FORCE_CHECKED", "int128-checked")):
+        monkeypatch.delenv("TBIRCH_FORCE_WIDE", raising=False)
+        monkeypatch.delenv("TBIRCH_FORCE_CHECKED", raising=False)
+        if env:
+            monkeypatch.setenv(env, "1")
+        g = Genus(t, precise=True)
+        try:
+            csr = g.hecke_matrix_sparse(p)
+            mode = g.last_int_mode()
+            rec = g.neighbor_records(p, 0, rows)
+            iso = None
+            if small:
+                seq = IsometrySequence(g, p)
+                iso = seq.read(t.N * (p + 1))
+                seq.close()
+        finally:
+            g.close()
+        assert mode == want_mode, (env, mode)
+        got[env] = (csr, rec, iso)
+    for env, (csr, rec, iso) in got.items():
+        assert np.array_equal(rec, got[None][1]), env
+        for cond in csr:
+            for a, b in zip(csr[cond], got[None][0][cond]):
+                assert np.array_equal(a, b), (env, cond)
+        if small:
+            assert np.array_equal(iso, got[None][2]), env
+    oracle = port_oracle(name)
+    assert_same_csr(got[None][0], oracle.hecke(p, True), name)
+    if small:
+        assert np.array_equal(got[None][1], oracle.neighbor_records(p, True)[:rows])
+        assert np.array_equal(got[None][2], oracle.isometry_sequence(p, True))
