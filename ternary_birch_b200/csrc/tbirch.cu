@@ -685,7 +685,7 @@ static bool precise_bounds_ok64(const tb_genus *g)
     if (!precise_bounds_ok(g) || !pc.narrow_trace || g->force_wide) return false;
     const double lp = log2((double)pc.p + 4.0);
     const double iso = 1 + lp + 0.5 * (g->log2_coef - log2(g->lambda_min));
-    return lp < 20 && g->log2_coef + 2 * lp < 58 && iso < 60;
+    return lp < 20 && g->log2_coef + 2 * lp < 56 && iso < 60;
 }
 
 template <int MODE>
