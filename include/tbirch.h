@@ -176,6 +176,30 @@ int tb_table_desc(const tb_table *t, tb_genus_desc *desc, const int64_t **parent
                   const int64_t **rep_prime, const int64_t **num_auts);
 void tb_table_destroy(tb_table *t);
 
+/* ---- modular linear algebra for the eigenvector search ----------------- */
+/* The consumer of T_p: the reference's
+ * BirchGenus.rational_eigenvectors (ternary_birch.pyx:246-379) asks Sage for
+ * (matrix - e).right_kernel(); these compute that kernel modulo a prime P < 2^29 on the
+ * GPU (panel-blocked Gauss-Jordan elimination); the Python layer lifts it to Q (CRT,
+ * rational reconstruction) and verifies it exactly.  The basis is the canonical one of the
+ * reduced row echelon form: one vector per free column f (ascending), with x[f] = 1 and 0 in
+ * the other free columns, so bases for different P agree entrywise modulo the P's. */
+typedef struct tb_modkernel tb_modkernel;
+/* right kernel {x : (A - shift I) x = 0 mod P} of an n x n CSR int32 matrix (host pointers) */
+int tb_modkernel_csr(const int32_t *data, const int32_t *indices, const int32_t *indptr, int64_t n,
+                     int64_t shift, uint32_t P, tb_modkernel **out);
+/* right kernel {x : M x = 0 mod P} of a dense rows x cols row-major int64 matrix (host pointer) */
+int tb_modkernel_dense(const int64_t *M, int64_t rows, int64_t cols, uint32_t P, tb_modkernel **out);
+int64_t tb_modkernel_dim(const tb_modkernel *k);
+int64_t tb_modkernel_cols(const tb_modkernel *k);
+/* free (non-pivot) columns, ascending: free_cols[dim] */
+int tb_modkernel_free_cols(const tb_modkernel *k, int64_t *free_cols);
+/* basis[dim][cols], residues in [0, P) */
+int tb_modkernel_basis(const tb_modkernel *k, uint32_t *basis);
+/* device time of the elimination in ms (CUDA events) */
+float tb_modkernel_ms(const tb_modkernel *k);
+void tb_modkernel_destroy(tb_modkernel *k);
+
 /* ---- integer-pipe microbenchmark -------------------------------------- */
 /* Measures the int32 issue peak used as the roofline denominator: runs an
  * unrolled IMAD + IADD3/LOP3 chain on every SM.  Returns int32 op/s. */

@@ -45,6 +45,18 @@ def lib() -> ctypes.CDLL:
     L.tb_launch_count.restype = u64
     L.tb_last_kernel_time.argtypes = [vp, vp, vp, vp]
     L.tb_last_int_mode.argtypes = [vp]
+    L.tb_modkernel_csr.argtypes = [vp, vp, vp, i64, i64, ctypes.c_uint32, vp]
+    L.tb_modkernel_dense.argtypes = [vp, i64, i64, ctypes.c_uint32, vp]
+    L.tb_modkernel_dim.argtypes = [vp]
+    L.tb_modkernel_dim.restype = i64
+    L.tb_modkernel_cols.argtypes = [vp]
+    L.tb_modkernel_cols.restype = i64
+    L.tb_modkernel_free_cols.argtypes = [vp, vp]
+    L.tb_modkernel_basis.argtypes = [vp, vp]
+    L.tb_modkernel_ms.argtypes = [vp]
+    L.tb_modkernel_ms.restype = ctypes.c_float
+    L.tb_modkernel_destroy.argtypes = [vp]
+    L.tb_modkernel_destroy.restype = None
     L.tb_genus_create.argtypes = [ctypes.POINTER(GenusDesc), ctypes.POINTER(vp)]
     L.tb_genus_destroy.argtypes = [vp]
     L.tb_genus_destroy.restype = None
@@ -98,6 +110,8 @@ EXPORTS = [
     "tb_hecke_copy_dense", "tb_hecke_destroy", "tb_eigenvalues", "tb_isoseq_open", "tb_isoseq_done",
     "tb_isoseq_next", "tb_isoseq_read", "tb_isoseq_close", "tb_neighbor_records", "tb_int_peak",
     "tb_quad_form", "tb_genus_enumerate", "tb_table_desc", "tb_table_destroy",
+    "tb_modkernel_csr", "tb_modkernel_dense", "tb_modkernel_dim", "tb_modkernel_cols", "tb_modkernel_free_cols",
+    "tb_modkernel_basis", "tb_modkernel_ms", "tb_modkernel_destroy",
 ]
 
 

@@ -387,6 +387,8 @@ class BirchGenus:
         else:
             table = build_genus_table(int(level), ramified_primes, seed)
             self.ramified_primes_ = prime_symbols(int(level), ramified_primes)[1]
+        if not hasattr(self, "ramified_primes_"):
+            self.ramified_primes_ = None                      # not recorded in a bare table
         self.table = table
         self.level_ = table.level
         self.dims = {int(c): int(d) for c, d in zip(table.conductors, table.dims)}
@@ -412,6 +414,9 @@ class BirchGenus:
 
     def seed(self):
         return self.seed_
+
+    def ramified_primes(self):                                # pyx:236-237
+        return self.ramified_primes_
 
     def next_good_prime(self, p):
         while True:
@@ -477,6 +482,21 @@ class BirchGenus:
             return self.hecke[p][conductor]
         raise Exception("No Hecke matrix associated to this conductor. How did this happen?")
 
+    def rational_eigenvectors(self, precise=True, sparse=None, force=False, log=None):   # pyx:246-379
+        """Rational eigenvectors of the Hecke algebra on every conductor's space, as dicts
+        {'vector', 'aps', 'conductor'}.  Kernels are computed modulo primes on the GPU and lifted
+        to Q with an exact check (ternary_birch_b200/eigen.py); Sage is not needed."""
+        if not force and self.eigenvectors is not None:
+            return self.eigenvectors
+        from . import eigen
+        self.eigenvectors, self.eigenvector_search_stats = eigen.rational_eigenvectors(
+            self, precise=precise, sparse=sparse, log=log)
+        self.reset_eigenvector_manager()
+        return self.eigenvectors
+
+    def reset_eigenvector_manager(self):                     # pyx:432-454
+        self._managers = {}
+
     def add_eigenvector(self, eigenvector):                  # pyx:383-388
         if self.eigenvectors is None:
             self.eigenvectors = []
@@ -502,7 +522,7 @@ class BirchGenus:
         if self.level_ % p == 0:
             raise Exception("Cannot compute eigenvalues at primes dividing the level.")
         if self.eigenvectors is None:
-            raise Exception("No eigenvectors: add_eigenvector() first (the rational eigenvector search is Sage-side).")
+            self.rational_eigenvectors()
         aps = self._get(bool(precise)).eigenvalues(self._manager(bool(precise)), p)
         for n, vec in enumerate(self.eigenvectors):
             vec["aps"][p] = aps[n]
@@ -517,6 +537,8 @@ class BirchGenus:
                 ps.append(p)
             else:
                 break
+        if self.eigenvectors is None:
+            self.rational_eigenvectors()
         for p in ps:
             if not force and all(p in vec["aps"] for vec in self.eigenvectors):
                 continue
@@ -536,3 +558,19 @@ class BirchGenus:
                                src=int(rec[10]), dst=int(rec[11]))
         finally:
             seq.close()
+
+    def __repr__(self):                                      # pyx:818-822
+        facs = " * ".join(str(int(p)) for p in self.table.primes)
+        return """Birch genus with level {} = {}
+Ramified primes = {}
+Dimensions = {}
+Seed = {}""".format(self.level_, facs, self.ramified_primes_, self.dims, self.seed_)
+
+    def __reduce__(self):                                    # pyx:824-827
+        return (BirchGenus, (self.level_, self.ramified_primes_, self.seed_), self.__getstate__())
+
+    def __getstate__(self):                                  # pyx:829-835
+        return dict(eigenvectors=list(self.eigenvectors) if self.eigenvectors is not None else None)
+
+    def __setstate__(self, state):                           # pyx:837-841
+        self.eigenvectors = list(state["eigenvectors"]) if state["eigenvectors"] is not None else None

@@ -1,0 +1,179 @@
+"""Rational eigenvector search (reference: ternary_birch.pyx:246-379).
+
+CPU: the lifting layer (CRT, rational reconstruction, exact verification) against a
+pure-Python elimination.  GPU: the modular kernels of csrc/tb_linalg.cuh against the same
+pure-Python elimination, and the whole search against the known answers (level 11: the
+eigenvector (2, -3) of the curve 11a) and the committed fixture of level 85085, whose
+vectors were found by independent exact linear algebra on the unmodified reference's T_p
+(tests/golden/make_golden.py)."""
+import json
+import random
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+from ternary_birch_b200 import eigen
+
+
+def nullspace_mod(rows, ncols, P):
+    """Reference elimination: canonical (reduced echelon) right-kernel basis modulo P."""
+    m = [[int(x) % P for x in r] for r in rows]
+    pivots = []
+    r = 0
+    for c in range(ncols):
+        piv = next((i for i in range(r, len(m)) if m[i][c]), None)
+        if piv is None:
+            continue
+        m[r], m[piv] = m[piv], m[r]
+        inv = pow(m[r][c], P - 2, P)
+        m[r] = [(x * inv) % P for x in m[r]]
+        for i in range(len(m)):
+            if i != r and m[i][c]:
+                f = m[i][c]
+                m[i] = [(x - f * y) % P for x, y in zip(m[i], m[r])]
+        pivots.append(c)
+        r += 1
+        if r == len(m):
+            break
+    free = [c for c in range(ncols) if c not in pivots]
+    basis = np.zeros((len(free), ncols), dtype=np.uint32 if P < (1 << 32) else object)
+    for k, fc in enumerate(free):
+        basis[k, fc] = 1
+        for i, pc in enumerate(pivots):
+            basis[k, pc] = (-m[i][fc]) % P
+    return tuple(free), basis
+
+
+def test_rational_reconstruct_and_lift():
+    m = 536870909 * 536870879
+    vals = [Fraction(3, 7), Fraction(-5, 21), Fraction(1), Fraction(0), Fraction(123456, 35)]
+    res = [(v.numerator * pow(v.denominator, -1, m)) % m for v in vals]
+    assert eigen.rational_reconstruct(res[0], m, 1 << 20) == (3, 7)
+    assert eigen.lift_vector(res, m) == [45, -25, 105, 0, 370368]
+    assert eigen.lift_vector(res, 1009) is None                     # modulus too small
+    assert eigen.normalize_vector([0, -4, 6]) == [0, 2, -3]
+    assert eigen.candidate_eigenvalues(2) == [0, -1, -2, 2, 1]
+    ps = eigen.lifting_primes()
+    assert [next(ps) for _ in range(3)] == [536870909, 536870879, 536870869]
+
+
+def test_rational_kernel_lifting_cpu():
+    """A 12 x 12 integer matrix with a planted 3-dimensional kernel whose reduced basis has
+    large rational entries: needs several primes, every vector verified over Z."""
+    rng = random.Random(5)
+    n, d = 12, 3
+    K = [[rng.randint(-50, 50) for _ in range(n)] for _ in range(d)]                  # kernel vectors
+    # rows orthogonal to the kernel: random combinations of a basis of K-perp
+    Q = (1 << 61) - 1
+    free, basis = nullspace_mod(K, n, Q)                                             # K x = 0 mod Q
+    perp = [eigen.lift_vector([int(x) for x in row], Q) for row in basis]
+    assert all(p is not None for p in perp) and len(perp) == n - d
+    coef = [[rng.randint(-3, 3) for _ in perp] for _ in range(n)]
+    A = [[sum(c * p[j] for c, p in zip(coef[i], perp)) for j in range(n)] for i in range(n)]
+    calls = []
+
+    def kernel_mod(P):
+        calls.append(P)
+        f, b = nullspace_mod(A, n, P)
+        return f, b, 0.0
+
+    def verify(v):
+        return all(sum(a * x for a, x in zip(row, v)) == 0 for row in A)
+    vecs, st = eigen.rational_kernel(kernel_mod, verify)
+    assert len(vecs) == d and len(calls) >= 2
+    for v in vecs:
+        assert verify(v) and eigen.normalize_vector(v) == v
+
+
+def random_matrix(rng, rows, cols, rank, P):
+    a = [[rng.randrange(P) for _ in range(rank)] for _ in range(rows)]
+    b = [[rng.randrange(P) for _ in range(cols)] for _ in range(rank)]
+    return [[sum(a[i][k] * b[k][j] for k in range(rank)) % P for j in range(cols)] for i in range(rows)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols,rank", [(1, 1, 0), (1, 1, 1), (5, 5, 5), (7, 3, 2), (3, 9, 3), (40, 40, 33),
+                                             (70, 131, 64), (200, 130, 97), (150, 150, 0), (129, 257, 129)])
+def test_modkernel_dense_vs_python(rows, cols, rank):
+    P = 536870909
+    rng = random.Random(rows * 1000 + cols)
+    M = random_matrix(rng, rows, cols, rank, P) if rank else [[0] * cols for _ in range(rows)]
+    # signed / unreduced input must be reduced by the library
+    Min = np.array([[x - P * ((i + j) % 3) for j, x in enumerate(r)] for i, r in enumerate(M)], dtype=np.int64)
+    free, basis, ms = eigen.kernel_mod_dense(Min, P)
+    wfree, wbasis = nullspace_mod(M, cols, P)
+    assert free == wfree
+    assert np.array_equal(basis, wbasis)
+
+
+@pytest.mark.gpu
+def test_modkernel_csr_shift_and_errors():
+    from scipy.sparse import random as sprandom
+    P = 536870879
+    n = 90
+    A = (sprandom(n, n, density=0.05, random_state=3, format="csr") * 20).astype(np.int32)
+    A.data -= 7
+    A.sort_indices()
+    for shift in (0, 3, -2):
+        free, basis, ms = eigen.kernel_mod_csr(A.data, A.indices, A.indptr, n, shift, P)
+        dense = A.toarray().astype(np.int64) - shift * np.eye(n, dtype=np.int64)
+        wfree, wbasis = nullspace_mod(dense.tolist(), n, P)
+        assert free == wfree and np.array_equal(basis, wbasis), shift
+    with pytest.raises(ValueError, match="prime"):
+        eigen.kernel_mod_csr(A.data, A.indices, A.indptr, n, 0, 1 << 28)
+    with pytest.raises(ValueError, match="prime"):
+        eigen.kernel_mod_dense(np.zeros((2, 2), dtype=np.int64), (1 << 29) + 11)
+
+
+@pytest.mark.gpu
+def test_rational_eigenvectors_level_11(tables):
+    """T_2 = [[1,2],[3,0]] has eigenvalues 3 (outside the Hasse interval of p = 2, so the search
+    drops it exactly as the reference does) and -2 with eigenvector (2, -3): the curve 11a."""
+    from ternary_birch_b200 import BirchGenus
+    b = BirchGenus(tables("11"))
+    vecs = b.rational_eigenvectors()
+    assert vecs == [dict(vector=[2, -3], aps={2: -2}, conductor=1)]
+    assert b.rational_eigenvectors() is vecs                     # cached (pyx:247-249)
+    assert b.compute_eigenvalues(3) == [-1] and b.compute_eigenvalues(5) == [1]
+    assert b.eigenvectors[0]["aps"] == {2: -2, 3: -1, 5: 1}
+
+
+@pytest.mark.gpu
+def test_rational_eigenvectors_c3(tables, port_oracle, golden_dir):
+    """Config 3 end to end without Sage: search, then compute_eigenvalues_upto(1000)."""
+    from scipy.sparse import csr_matrix
+    from ternary_birch_b200 import BirchGenus
+    gold = json.load(open(golden_dir / "eigen_85085.json"))
+    b = BirchGenus(tables("85085"))
+    vecs = b.rational_eigenvectors(precise=True)
+    got = {(v["conductor"], tuple(v["vector"])) for v in vecs}
+    assert len(got) == len(vecs)
+    # the fixture's vectors, minus the Eisenstein vector (eigenvalue p + 1 lies outside the Hasse interval)
+    want = {(v["conductor"], tuple(v["vector"])) for v in gold["vectors"] if len(set(v["vector"])) > 1}
+    assert want <= got
+    # every vector found is an exact simultaneous eigenvector of the oracle's T_2, T_3, T_19
+    t = tables("85085")
+    oracle = port_oracle("85085")
+    for p in (2, 3, 19):
+        mats = {m["conductor"]: csr_matrix((m["data"], m["indices"], m["indptr"]), shape=(m["dim"], m["dim"]))
+                for m in oracle.hecke(p, True)}
+        for v in vecs:
+            w = eigen.csr_matvec_exact(mats[v["conductor"]], v["vector"])
+            nz = next(i for i, x in enumerate(v["vector"]) if x)
+            lam = w[nz] // v["vector"][nz]
+            assert all(a == lam * x for a, x in zip(w, v["vector"]))
+            assert abs(lam) <= int(2 * p ** 0.5)
+            if p in v["aps"]:
+                assert v["aps"][p] == lam
+            assert eigen.normalize_vector(v["vector"]) == v["vector"]
+    # a_p of the fixture vectors through the eigenvalue kernel agree with the reference's
+    b.compute_eigenvalues_upto(100, precise=False)
+    index = {(v["conductor"], tuple(v["vector"])): i for i, v in enumerate(vecs)}
+    for j, v in enumerate(gold["vectors"]):
+        key = (v["conductor"], tuple(v["vector"]))
+        if key not in index:
+            continue
+        for p in gold["primes"]:
+            if p <= 100:
+                assert b.eigenvectors[index[key]]["aps"][p] == gold["aps_z64"][str(p)][j], (key[0], p)
