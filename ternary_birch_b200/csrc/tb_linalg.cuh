@@ -6,12 +6,13 @@
 // panel-blocked Gauss-Jordan elimination and lifted to Q on the host (CRT over several P,
 // rational reconstruction, exact verification over Z).
 //
-// Layout: M is rows x ld uint32 (row-major, ld a multiple of 128, residues in [0, P)).
+// Layout: M is rows x ld uint32 (row-major, ld a multiple of 128), Montgomery residues x 2^32 mod P.
 // One panel = TB_LA_PANEL consecutive columns:
 //   panel_kernel     a cooperative grid walks the panel's columns: picks a pivot row (any unused row
-//                    with a non-zero entry -- exact arithmetic, so any pivot is fine), scales
-//                    it, eliminates the column from every other row inside the panel and
-//                    records the multipliers L[row][j]
+//                    with a non-zero entry -- exact arithmetic, so any pivot is fine),
+//                    eliminates the column from every other row inside the panel and
+//                    records the multipliers L[row][j]; one grid barrier per column
+//   pivot_fix_kernel scales the panel's pivot rows, sorts out their multipliers
 //   pivot_rows_kernel applies the same row operations to the pivot rows' other columns
 //                    (a TB_LA_PANEL-step triangular recurrence per column) -> R[j][col]
 //   update_kernel    rank-TB_LA_PANEL update of every other row and column:
@@ -35,7 +36,7 @@ namespace cg = cooperative_groups;
 #define TB_LA_TILE_COLS 128
 
 struct LaCtx {
-    u32 *M;          // rows x ld
+    u32 *M;          // rows x ld, Montgomery residues
     u32 *L;          // rows x TB_LA_PANEL multipliers of the current panel
     u32 *R;          // TB_LA_PANEL x ld transformed pivot rows of the current panel
     int *row_pivot;  // [rows] pivot index owned by the row, -1 if none
@@ -43,73 +44,82 @@ struct LaCtx {
     int *piv_col;
     int *rank;       // device counter
     int *panel_piv;  // [TB_LA_PANEL] pivot row of each panel step, -1 = free column
-    u32 *panel_lp;   // [TB_LA_PANEL][TB_LA_PANEL] multipliers of pivot rows at earlier steps
+    u32 *panel_lp;   // [TB_LA_PANEL][TB_LA_PANEL] multipliers a pivot row received before its own step
     u32 *panel_inv;  // [TB_LA_PANEL] inverse of each pivot
     int rows, cols, ld;
     u32 P;
-    InvDiv dP;
+    u32 Pneg_inv;    // -P^-1 mod 2^32
+    u32 R2;          // 2^64 mod P
+    u32 one;         // 2^32 mod P (Montgomery 1)
+    u32 magic;       // floor(2^32 / P)
 };
 
-__device__ __forceinline__ u32 la_mod(u64 x, const InvDiv &dP)
+// Montgomery arithmetic modulo P < 2^29 with R = 2^32: residues are kept as x R mod P, a
+// product costs IMAD.WIDE + IMAD.LO + IMAD.WIDE + compare/subtract.
+__device__ __forceinline__ u32 la_redc(u64 t, const LaCtx &c)      // t < P 2^32  ->  t / R mod P
 {
-    u64 r;
-    udivmod(x, dP, r);
-    return (u32)r;
+    const u32 m = (u32)t * c.Pneg_inv;
+    const u32 r = (u32)((t + (u64)m * c.P) >> 32);
+    return r >= c.P ? r - c.P : r;
 }
-__device__ __forceinline__ u32 la_mul(u32 a, u32 b, const InvDiv &dP) { return la_mod((u64)a * b, dP); }
-__device__ __forceinline__ u32 la_inv(u32 a, u32 P, const InvDiv &dP)
+__device__ __forceinline__ u32 la_mul(u32 a, u32 b, const LaCtx &c) { return la_redc((u64)a * b, c); }
+__device__ __forceinline__ u32 la_sub(u32 a, u32 b, const LaCtx &c) { return a >= b ? a - b : a + c.P - b; }
+// any 64-bit accumulator of Montgomery products -> its Montgomery residue
+__device__ __forceinline__ u32 la_fold(u64 acc, const LaCtx &c)
 {
-    u32 r = 1, e = P - 2;
+    const u32 r = (u32)(acc >> 32) + la_redc((u64)(u32)acc, c);     // < 2^32 + P fits: acc >> 32 < 2^31 here
+    const u32 q = __umulhi(r, c.magic);
+    const u32 v = r - q * c.P;                                       // < 2 P
+    return v >= c.P ? v - c.P : v;
+}
+__device__ __forceinline__ u32 la_inv(u32 a, const LaCtx &c)        // Fermat, in the Montgomery domain
+{
+    u32 r = c.one, e = c.P - 2;
     while (e)
     {
-        if (e & 1u) r = la_mul(r, a, dP);
-        a = la_mul(a, a, dP);
+        if (e & 1u) r = la_mul(r, a, c);
+        a = la_mul(a, a, c);
         e >>= 1;
     }
     return r;
 }
-
-// dense M from CSR int32 (A - shift * I), residues mod P
-__global__ void la_zero_kernel(u32 *M, size_t words)
+__device__ __forceinline__ u32 la_to_mont(i64 v, const LaCtx &c)
 {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < words; i += stride) M[i] = 0;
+    v %= (i64)c.P;
+    if (v < 0) v += (i64)c.P;
+    return la_mul((u32)v, c.R2, c);
 }
+
+// dense M from CSR int32 (A - shift * I)
 __global__ void la_from_csr_kernel(LaCtx c, const int *data, const int *indices, const int *indptr, i64 shift)
 {
     const int row = blockIdx.x;
     u32 *Mr = c.M + (size_t)row * c.ld;
-    const i64 P = (i64)c.P;
+    __shared__ i64 s_diag;
+    if (threadIdx.x == 0) s_diag = 0;
+    __syncthreads();
     for (int k = indptr[row] + threadIdx.x; k < indptr[row + 1]; k += blockDim.x)
     {
-        i64 v = (i64)data[k] % P;
-        if (v < 0) v += P;
-        Mr[indices[k]] = (u32)v;
+        if (indices[k] == row) s_diag = (i64)data[k];
+        else Mr[indices[k]] = la_to_mont((i64)data[k], c);
     }
     __syncthreads();
-    if (threadIdx.x == 0 && row < c.cols)
-    {
-        i64 v = ((i64)Mr[row] - shift % P) % P;
-        if (v < 0) v += P;
-        Mr[row] = (u32)v;
-    }
+    if (threadIdx.x == 0 && row < c.cols) Mr[row] = la_to_mont(s_diag % (i64)c.P - shift % (i64)c.P, c);
 }
 __global__ void la_from_dense_kernel(LaCtx c, const i64 *src)
 {
     const int row = blockIdx.y;
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= c.cols) return;
-    const i64 P = (i64)c.P;
-    i64 v = src[(size_t)row * c.cols + col] % P;
-    if (v < 0) v += P;
-    c.M[(size_t)row * c.ld + col] = (u32)v;
+    c.M[(size_t)row * c.ld + col] = la_to_mont(src[(size_t)row * c.cols + col], c);
 }
 
-// Cooperative grid (one CTA per SM at most); global warp gw handles rows gw, gw + GW, ...;
-// lane = column inside the panel.  Two grid barriers per pivot step: after the elimination
-// pass (so the scaled pivot row may replace the unscaled one everyone read) and after that
-// write (the next step eliminates the old pivot row like any other row).
+// Cooperative grid; global warp gw handles rows gw, gw + GW, ...; lane = column inside the
+// panel.  ONE grid barrier per pivot step: pivot rows stay unscaled in M for the whole panel
+// (every CTA derives the scaled row it eliminates with from the unscaled one, which nobody
+// writes during that step), and rows are eliminated uniformly whether or not they were a
+// pivot before: u -= u[j] * scaled_pivot_row is the same update on a scaled or unscaled row.
+// The final scaling of the panel's pivot rows happens in la_pivot_fix_kernel.
 __device__ __forceinline__ void la_search_column(const LaCtx &c, int col, int gw, int GW, int lane, int *cand)
 {
     // smallest unused row with a non-zero entry in `col`: lanes test 32 rows at a time
@@ -130,7 +140,6 @@ __global__ void __launch_bounds__(TB_LA_PANEL_THREADS) la_panel_kernel(LaCtx c, 
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ u32 s_prow[TB_LA_PANEL];
-    __shared__ u32 s_inv;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int gw = blockIdx.x * wpb + warp, GW = gridDim.x * wpb;
     const int width = min(TB_LA_PANEL, c.cols - c0);
@@ -142,7 +151,6 @@ __global__ void __launch_bounds__(TB_LA_PANEL_THREADS) la_panel_kernel(LaCtx c, 
     {
         if (threadIdx.x <= TB_LA_PANEL) cand[threadIdx.x] = 0x7fffffff;
         if (threadIdx.x < TB_LA_PANEL) c.panel_piv[threadIdx.x] = -1;
-        for (int i = threadIdx.x; i < TB_LA_PANEL * TB_LA_PANEL; i += blockDim.x) c.panel_lp[i] = 0;
     }
     grid.sync();
     la_search_column(c, c0, gw, GW, lane, &cand[0]);
@@ -159,14 +167,21 @@ __global__ void __launch_bounds__(TB_LA_PANEL_THREADS) la_panel_kernel(LaCtx c, 
             continue;
         }
 
-        // every CTA derives the scaled pivot row from the (still unscaled) row in M
         if (warp == 0)
         {
-            const u32 pv = c.M[(size_t)piv * c.ld + c0 + j];
-            const u32 inv = la_inv(pv, c.P, c.dP);
             const u32 x = live ? c.M[(size_t)piv * c.ld + c0 + lane] : 0u;
-            s_prow[lane] = la_mul(x, inv, c.dP);
-            if (lane == 0) s_inv = inv;
+            const u32 inv = la_inv(__shfl_sync(0xffffffffu, x, j), c);
+            s_prow[lane] = la_mul(x, inv, c);
+            if (gw == 0 && lane == 0)
+            {
+                const int k = *c.rank;
+                c.piv_row[k] = piv;
+                c.piv_col[k] = c0 + j;
+                c.row_pivot[piv] = k;
+                *c.rank = k + 1;
+                c.panel_piv[j] = piv;
+                c.panel_inv[j] = inv;
+            }
         }
         __syncthreads();
         const u32 pr = s_prow[lane];
@@ -182,8 +197,7 @@ __global__ void __launch_bounds__(TB_LA_PANEL_THREADS) la_panel_kernel(LaCtx c, 
             if (f != 0)
             {
                 if (lane == j) c.L[(size_t)row * TB_LA_PANEL + j] = f;
-                const u32 sub = la_mul(f, pr, c.dP);
-                x = x >= sub ? x - sub : x + c.P - sub;
+                x = la_sub(x, la_mul(f, pr, c), c);
                 if (live) Mr[lane] = x;
             }
             if (j + 1 < width && next == 0x7fffffff)
@@ -194,28 +208,30 @@ __global__ void __launch_bounds__(TB_LA_PANEL_THREADS) la_panel_kernel(LaCtx c, 
         }
         if (lane == 0 && next != 0x7fffffff) atomicMin(&cand[j + 1], next);
         grid.sync();
-
-        if (gw == 0)
-        {
-            // scaled pivot row replaces the unscaled one; the multipliers it received at earlier
-            // steps feed the pivot-row recurrence and it takes no part in the rank update
-            if (live) c.M[(size_t)piv * c.ld + c0 + lane] = pr;
-            const u32 lp = c.L[(size_t)piv * TB_LA_PANEL + lane];
-            c.panel_lp[j * TB_LA_PANEL + lane] = lane < j ? lp : 0u;
-            c.L[(size_t)piv * TB_LA_PANEL + lane] = 0;
-            if (lane == 0)
-            {
-                const int k = *c.rank;
-                c.piv_row[k] = piv;
-                c.piv_col[k] = c0 + j;
-                c.row_pivot[piv] = k;
-                *c.rank = k + 1;
-                c.panel_piv[j] = piv;
-                c.panel_inv[j] = s_inv;
-            }
-        }
-        grid.sync();
     }
+}
+
+// After the panel: scale the panel's pivot rows inside the panel, and split the multipliers a
+// pivot row collected into those it received before its own step (they drive the pivot-row
+// recurrence) and those after it (scaled, they take part in the rank update like any row's).
+__global__ void la_pivot_fix_kernel(LaCtx c, int c0)
+{
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;     // one warp per panel step
+    const int piv = c.panel_piv[k];
+    u32 lp = 0;
+    if (piv >= 0)
+    {
+        const u32 inv = c.panel_inv[k];
+        const u32 l = c.L[(size_t)piv * TB_LA_PANEL + lane];
+        lp = lane < k ? l : 0u;
+        c.L[(size_t)piv * TB_LA_PANEL + lane] = lane > k ? la_mul(l, inv, c) : 0u;
+        if (c0 + lane < c.cols)
+        {
+            u32 *m = c.M + (size_t)piv * c.ld + c0 + lane;
+            *m = la_mul(*m, inv, c);
+        }
+    }
+    c.panel_lp[k * TB_LA_PANEL + lane] = lp;
 }
 
 // R[j][col] = the panel's pivot rows after the panel's row operations, for the columns
@@ -246,10 +262,8 @@ __global__ void la_pivot_rows_kernel(LaCtx c, int c0)
             u64 acc = 0;
 #pragma unroll
             for (int j = 0; j < k; ++j) acc += (u64)s_lp[k * TB_LA_PANEL + j] * xp[j];
-            const u32 sub = la_mod(acc, c.dP);
-            u32 x = c.M[(size_t)piv * c.ld + col];
-            x = x >= sub ? x - sub : x + c.P - sub;
-            v = la_mul(x, s_inv[k], c.dP);
+            const u32 x = la_sub(c.M[(size_t)piv * c.ld + col], la_fold(acc, c), c);
+            v = la_mul(x, s_inv[k], c);
             c.M[(size_t)piv * c.ld + col] = v;
         }
         xp[k] = v;
@@ -316,8 +330,7 @@ __global__ void __launch_bounds__(256) la_update_kernel(LaCtx c, int c0, const i
             {
                 const int cc = col + b;
                 if (cc >= c0 && cc < c0 + TB_LA_PANEL) continue;      // panel columns are final already
-                const u32 sub = la_mod(acc[a][h * 4 + b], c.dP);
-                mv[b] = mv[b] >= sub ? mv[b] - sub : mv[b] + c.P - sub;
+                mv[b] = la_sub(mv[b], la_fold(acc[a][h * 4 + b], c), c);
             }
             *ptr = make_uint4(mv[0], mv[1], mv[2], mv[3]);
         }
@@ -333,7 +346,7 @@ __global__ void la_kernel_basis_kernel(LaCtx c, const int *free_col, int dim, in
     const int fc = free_col[m];
     if (k == 0) basis[(size_t)m * c.cols + fc] = 1;
     if (k >= rank) return;
-    const u32 v = c.M[(size_t)c.piv_row[k] * c.ld + fc];
+    const u32 v = la_redc((u64)c.M[(size_t)c.piv_row[k] * c.ld + fc], c);      // out of the Montgomery domain
     basis[(size_t)m * c.cols + c.piv_col[k]] = v ? c.P - v : 0u;
 }
 

@@ -1552,7 +1552,14 @@ static int la_solve(int64_t rows, int64_t cols, uint32_t P, Fill fill, tb_modker
     c.rows = (int)rows; c.cols = (int)cols;
     c.ld = (int)((cols + TB_LA_TILE_COLS - 1) / TB_LA_TILE_COLS * TB_LA_TILE_COLS);
     c.P = P;
-    c.dP = make_invdiv(P);
+    {
+        u32 inv = P;                                   // Newton: P * inv = 1 mod 2^32
+        for (int i = 0; i < 5; ++i) inv *= 2u - P * inv;
+        c.Pneg_inv = 0u - inv;
+        c.one = (u32)(((u64)1 << 32) % P);
+        c.R2 = (u32)(((u64)c.one * c.one) % P);
+        c.magic = (u32)(((u64)1 << 32) / P);
+    }
     const int tiles = c.ld / TB_LA_TILE_COLS;
     const int maxpiv = (int)std::min(rows, cols);
     LaBuf<u32> M, L, R, lp, inv;
@@ -1586,17 +1593,19 @@ static int la_solve(int64_t rows, int64_t cols, uint32_t P, Fill fill, tb_modker
         TB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, la_panel_kernel, TB_LA_PANEL_THREADS, 0));
         const int warps_per_block = TB_LA_PANEL_THREADS / 32;
-        int grid = (int)std::min<int64_t>((int64_t)sms * std::max(per_sm, 1), (rows + warps_per_block - 1) / warps_per_block);
-        grid = std::max(1, std::min(grid, sms));
+        // co-resident by construction; a few CTAs per SM keep the per-warp row loop short
+        int grid = (int)std::min<int64_t>((int64_t)sms * std::min(std::max(per_sm, 1), 4), (rows + warps_per_block - 1) / warps_per_block);
+        grid = std::max(1, grid);
         const dim3 ugrid(tiles, (unsigned)((rows + TB_LA_TILE_ROWS - 1) / TB_LA_TILE_ROWS));
         for (int c0 = 0; c0 < c.cols; c0 += TB_LA_PANEL)
         {
             int *cand_ptr = cand.ptr, *tf_ptr = tile_free.ptr;
             void *args[] = {(void *)&c, (void *)&c0, (void *)&cand_ptr, (void *)&tf_ptr};
             TB_CUDA(cudaLaunchCooperativeKernel((void *)la_panel_kernel, dim3(grid), dim3(TB_LA_PANEL_THREADS), args, 0, 0));
+            la_pivot_fix_kernel<<<1, TB_LA_PANEL * 32>>>(c, c0);
             la_pivot_rows_kernel<<<(c.cols + 127) / 128, 128>>>(c, c0);
             la_update_kernel<<<ugrid, 256>>>(c, c0, tile_free.ptr);
-            g_launches += 3;
+            g_launches += 4;
         }
         TB_CUDA(cudaGetLastError());
     }
