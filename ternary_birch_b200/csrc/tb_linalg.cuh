@@ -31,7 +31,7 @@ namespace tb {
 namespace cg = cooperative_groups;
 
 #define TB_LA_PANEL 32
-#define TB_LA_PANEL_THREADS 256
+#define TB_LA_PANEL_THREADS 1024
 #define TB_LA_TILE_ROWS 64
 #define TB_LA_TILE_COLS 128
 

@@ -1594,7 +1594,7 @@ static int la_solve(int64_t rows, int64_t cols, uint32_t P, Fill fill, tb_modker
         TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, la_panel_kernel, TB_LA_PANEL_THREADS, 0));
         const int warps_per_block = TB_LA_PANEL_THREADS / 32;
         // co-resident by construction; a few CTAs per SM keep the per-warp row loop short
-        int grid = (int)std::min<int64_t>((int64_t)sms * std::min(std::max(per_sm, 1), 4), (rows + warps_per_block - 1) / warps_per_block);
+        int grid = (int)std::min<int64_t>((int64_t)sms * std::min(std::max(per_sm, 1), 1), (rows + warps_per_block - 1) / warps_per_block);
         grid = std::max(1, grid);
         const dim3 ugrid(tiles, (unsigned)((rows + TB_LA_TILE_ROWS - 1) / TB_LA_TILE_ROWS));
         for (int c0 = 0; c0 < c.cols; c0 += TB_LA_PANEL)

@@ -1,0 +1,175 @@
+"""Result persistence: the sqlite eigenvector database
+(reference: src/sage/build_database.py) and the per-level JSON documents
+(reference: scripts/generate_eigenvalues.py).
+
+CPU: schema, packing, duplicate removal, job generation and the JSON layout against a stub
+genus.  GPU: the whole batch flow on small levels, checked against FIRST-PRINCIPLES known
+answers: by modularity the rational eigenvectors at a squarefree level are the isogeny
+classes of elliptic curves of that conductor, and a_p = p + 1 - #E(F_p) is counted here
+directly from Cremona's minimal models."""
+import json
+import sqlite3
+
+import pytest
+
+from ternary_birch_b200 import batch
+from ternary_birch_b200.database import EigenvectorDatabase
+
+
+class StubGenus:
+    """The slice of BirchGenus the persistence layer touches."""
+    calls = []
+
+    def __init__(self, level, ramified_primes=None, seed=None):
+        StubGenus.calls.append((level, ramified_primes, seed))
+        self.level_, self.seed_ = int(level), 77 if seed is None else seed
+        primes = batch.prime_divisors(self.level_)
+        self.ramified_primes_ = list(ramified_primes) if ramified_primes else (primes[:-1] if len(primes) % 2 == 0 else primes)
+        self.eigenvectors = None
+        self.resets = 0
+
+    def level(self):
+        return self.level_
+
+    def seed(self):
+        return self.seed_
+
+    def ramified_primes(self):
+        return self.ramified_primes_
+
+    def dimensions(self):
+        return {1: 3, self.level_: 2}
+
+    def dimension(self):
+        return 5
+
+    def rational_eigenvectors(self, precise=True):
+        if self.eigenvectors is None:
+            q = self.level_ // self.ramified_primes_[0] if len(batch.prime_divisors(self.level_)) == 2 else 1
+            self.eigenvectors = [dict(vector=[1, -2, 0], aps={2: -1}, conductor=1),
+                                 dict(vector=[0, 3, 1], aps={2: 1}, conductor=1)]
+            if q > 1:                                   # an oldform pair: conductors d and d * q, same a_p
+                self.eigenvectors += [dict(vector=[5, 5], aps={2: 2}, conductor=self.ramified_primes_[0]),
+                                      dict(vector=[1, 4], aps={2: 2}, conductor=self.level_)]
+        return self.eigenvectors
+
+    def add_eigenvector(self, vec):
+        if self.eigenvectors is None:
+            self.eigenvectors = []
+        self.eigenvectors.append(dict(vec))
+
+    def reset_eigenvector_manager(self):
+        self.resets += 1
+
+    def compute_eigenvalues_upto(self, upper, precise=True):
+        for v in self.rational_eigenvectors():
+            for p in (3, 5, 7):
+                if p <= upper and self.level_ % p:
+                    v["aps"][p] = v["aps"][2] * p
+
+
+def test_database_schema_and_roundtrip(tmp_path):
+    path = tmp_path / "eigenvectors.sqlite3"
+    with EigenvectorDatabase(str(path), genus_factory=StubGenus) as db:
+        g = db.get_genus_with_eigenvectors(33, precise=False)        # 3 * 11: two primes -> oldform removal
+        assert [v["conductor"] for v in g.eigenvectors] == [1, 1] and g.resets == 1
+        assert all("vector_id" in v for v in g.eigenvectors)
+        g.eigenvectors[0]["aps"][13] = 99
+        db.update_database_from_genus(g, precise=False)
+        g2 = db.get_genus_with_eigenvectors(30, precise=False, remove_oldforms=True)   # three primes: nothing removed
+        assert len(g2.eigenvectors) == 2 and g2.resets == 0
+        db.commit()
+    conn = sqlite3.connect(str(path))
+    cols = {t: [r[1] for r in conn.execute(f"PRAGMA table_info({t})")] for t in ("genus", "eigenvectors", "eigenvalues")}
+    assert cols == dict(genus=["level", "ramified_primes", "num_eigenvectors", "seed"],
+                        eigenvectors=["id", "level", "conductor", "vector"],
+                        eigenvalues=["vector_id", "p", "value"])
+    assert conn.execute("SELECT level, ramified_primes, num_eigenvectors, seed FROM genus ORDER BY level").fetchall() == \
+        [(30, "2,3,5", 2, 77), (33, "3", 2, 77)]
+    assert conn.execute("SELECT vector FROM eigenvectors WHERE level=33 ORDER BY id").fetchall() == [("1,-2,0",), ("0,3,1",)]
+    assert (1, 13, 99) in conn.execute("SELECT vector_id, p, value FROM eigenvalues").fetchall()
+    conn.close()
+    # a second session rebuilds the genus from the stored parameters and reloads the vectors
+    StubGenus.calls.clear()
+    with EigenvectorDatabase(str(path), genus_factory=StubGenus) as db:
+        g = db.get_genus_with_eigenvectors(33, precise=False)
+        assert StubGenus.calls == [(33, [3], 77)]
+        assert [v["vector"] for v in g.eigenvectors] == [[1, -2, 0], [0, 3, 1]]
+        assert g.eigenvectors[0]["aps"][13] == 99 and g.eigenvectors[0]["aps"][2] == -1
+        with pytest.raises(Exception, match="No genus found"):
+            db.update_database_from_genus(StubGenus(35), precise=False)
+    assert EigenvectorDatabase.unpack_vector(EigenvectorDatabase.pack_vector((3, -4, 0))) == [3, -4, 0]
+    assert EigenvectorDatabase.identify_duplicates(
+        [dict(conductor=1, aps={2: 0}), dict(conductor=3, aps={2: 1, 5: 2}), dict(conductor=33, aps={2: 1, 7: 0}),
+         dict(conductor=33, aps={2: -1})], 11) == [2, 1]
+
+
+def test_job_generation_and_json(tmp_path):
+    assert [batch.sturm_bound(n) for n in (11, 13, 379, 99)] == [2, 3, 64, 24]
+    assert batch.is_squarefree(30, num_primes=3) and not batch.is_squarefree(12) and not batch.is_squarefree(30, num_primes=2)
+    job = batch.generate_jobs(11 * 13, seed=3)
+    assert (job.ramified_primes, job.unramified_primes, job.ramified_primes_product) == ([11], [13], 11)
+    assert job.sturm_bound_of_ramified_primes_product == 2 and job.eigenvalues_upto == 2
+    job = batch.generate_jobs(2 * 3 * 5, seed=3, upto=5)
+    assert (job.ramified_primes, job.unramified_primes, job.eigenvalues_upto) == ([2, 3, 5], [], 5)
+    assert batch.generate_jobs(2 * 3 * 5, seed=3, upto=10 ** 6).eigenvalues_upto == batch.sturm_bound(30)
+    res = batch.find_rational_eigenvectors(batch.generate_jobs(1001, seed=9, upto=7), genus_factory=StubGenus)
+    path = tmp_path / "1001.json"
+    path.write_text(res.json())
+    doc = json.loads(path.read_text())
+    assert list(doc) == ["job", "dimensions_by_conductor", "dimension_total", "rational_eigenvectors_count",
+                         "rational_eigenvectors"]
+    assert list(doc["job"])[:8] == ["level", "seed", "ramified_primes", "ramified_primes_product", "unramified_primes",
+                                    "unramified_primes_product", "sturm_bound_of_ramified_primes_product",
+                                    "eigenvalues_upto"]
+    assert doc["job"]["elapsed_seconds"] >= doc["job"]["elapsed_seconds_eigenvalues"] >= 0
+    back = batch.load_result(path)
+    assert back["dimensions_by_conductor"] == {1: 3, 1001: 2} and back["rational_eigenvectors_count"] == 2
+    assert back["rational_eigenvectors"][0] == dict(vector=[1, -2, 0], aps={2: -1, 3: -3, 5: -5}, conductor=1)
+
+
+# Cremona minimal models [a1, a2, a3, a4, a6], one per isogeny class of the conductor
+CURVES = {
+    11: [[0, -1, 1, -10, -20]],
+    14: [[1, 0, 1, 4, -6]],
+    15: [[1, 1, 1, -10, -10]],
+    26: [[1, 0, 1, -5, -8], [1, -1, 1, -3, 3]],
+    30: [[1, 0, 1, 1, 2]],
+    37: [[0, 0, 1, -1, 0], [0, 1, 1, -23, -50]],
+}
+
+
+def trace_of_frobenius(curve, p):
+    a1, a2, a3, a4, a6 = curve
+    count = 1                                            # the point at infinity
+    for x in range(p):
+        rhs = (x * x * x + a2 * x * x + a4 * x + a6) % p
+        for y in range(p):
+            if (y * y + a1 * x * y + a3 * y - rhs) % p == 0:
+                count += 1
+    return p + 1 - count
+
+
+@pytest.mark.gpu
+def test_batch_flow_against_elliptic_curves(tmp_path):
+    """scripts/generate_eigenvalues.py's per-level job and build_database.py's flow, on real genera
+    built on the GPU.  Levels with two prime factors exercise the oldform removal."""
+    primes = [p for p in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31)]
+    with EigenvectorDatabase(str(tmp_path / "e.sqlite3")) as db:
+        for level, curves in CURVES.items():
+            genus = db.get_genus_with_eigenvectors(level, precise=False, remove_oldforms=True)
+            vecs = genus.rational_eigenvectors()
+            genus.compute_eigenvalues_upto(31, precise=False)
+            db.update_database_from_genus(genus, precise=False)
+            good = [p for p in primes if level % p]
+            got = sorted(tuple(v["aps"][p] for p in good) for v in vecs)
+            want = sorted(tuple(trace_of_frobenius(c, p) for p in good) for c in curves)
+            assert got == want, level
+        db.commit()
+        again = db.get_genus_with_eigenvectors(37, precise=False)
+        assert sorted(v["aps"][2] for v in again.eigenvectors) == [-2, 0]
+        assert again.compute_eigenvalues(41, precise=True) is not None
+    res = batch.find_rational_eigenvectors(batch.generate_jobs(37, seed=1))
+    assert res.rational_eigenvectors_count == 2 and res.dimension_total == sum(res.dimensions_by_conductor.values())
+    assert res.job.eigenvalues_upto == batch.sturm_bound(37) == 7
+    assert sorted(v["aps"][7] for v in res.rational_eigenvectors) == [-1, -1]
