@@ -115,10 +115,26 @@ int64_t tb_hecke_nnz(const tb_hecke *h, int64_t k);
 /* CSR triple in the reference's order (data, indices, indptr), Genus.h:662-671:
  * data[nnz], indices[nnz], indptr[rows+1]. */
 int tb_hecke_copy_sparse(tb_hecke *h, int64_t k, int32_t *data, int32_t *indices, int32_t *indptr);
-/* Same copy, enqueued on `cuda_stream` without synchronising (destinations must be device or
- * pinned host memory): lets the caller overlap the read-back of one T_p with the next one. */
+/* Same copy without synchronising: lets the caller overlap the read-back of one T_p with the
+ * next one.  Device destinations and small matrices are enqueued on `cuda_stream`; large host
+ * destinations are served by the library's background read-back.  Either way
+ * tb_hecke_copy_wait(h) is the completion point. */
 int tb_hecke_copy_sparse_async(tb_hecke *h, int64_t k, int32_t *data, int32_t *indices, int32_t *indptr,
                                void *cuda_stream);
+/* Blocks until every asynchronous copy of `h` issued so far has landed: the event of the last
+ * stream-ordered copy, and the background read-back of large host copies (which runs on the
+ * library's own copy stream and host threads, not on the caller's stream). */
+int tb_hecke_copy_wait(tb_hecke *h);
+/* Bytes that cross PCIe when data + indices + indptr of conductor k are read back to host
+ * memory (diagnostic for bench.py's d2h_bytes_per_step).  Host read-backs of large matrices go
+ * through a 3-byte-per-entry device format (uint16 column, int8 entry) that the library widens
+ * on the host; the arrays the caller receives are the reference's int32 CSR either way. */
+int64_t tb_hecke_transfer_bytes(const tb_hecke *h, int64_t k);
+/* Host-side widening throughput of this machine (no GPU involved; diagnostic): output GB/s of the
+ * library's thread pool on `entries` packed entries, the pool size, and whether the AVX2
+ * streaming-store path is in use. */
+int tb_host_widen_probe(int64_t entries, double *out_gbps, int *threads, int *avx2);
+
 /* Row-major rows x dim block, Genus.h:811-846. */
 int tb_hecke_copy_dense(tb_hecke *h, int64_t k, int32_t *matrix);
 void tb_hecke_destroy(tb_hecke *h);

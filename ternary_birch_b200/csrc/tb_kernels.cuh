@@ -314,6 +314,9 @@ struct RowLaunch {
     u64 *lookback;         // [2^K][rows] (flag << 62) | count, zeroed before launch (FUSED)
     int *ticket;           // row dispenser, zeroed before launch (FUSED)
     i64 *nnz_out;          // [2^K] written by the last row (FUSED)
+    int *maxmult;          // max number of neighbors of one row in one class = max |entry| (narrow read-back)
+    unsigned short *idx16; // optional narrow twins of indices / data for the read-back over PCIe
+    signed char *dat8;     //   (valid when every dim <= 65536 and maxmult <= 127), same offsets
     int *data;
     int *indices;
 };
@@ -437,6 +440,16 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
     __shared__ u64 s_partab[1024];                             // parity table of the current conductor chunk (K <= 10)
     const bool use_tab = L.K <= 10;
 
+    if (MODE != ROWS_FILL && L.maxmult)
+    {
+        // the largest run bounds every |entry| of the row in every conductor
+        int mx = 0;
+        for (int j = tid; j < ncols; j += nt)
+            mx = max(mx, ((j + 1 < ncols) ? start[j + 2] : nvalid) - start[j + 1]);
+        for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0 && mx > *(volatile int *)L.maxmult) atomicMax(L.maxmult, mx);
+    }
+
     for (int kc = 0; kc < C; kc += 8)
     {
         const int nk = min(8, C - kc);
@@ -549,6 +562,11 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
                         const i64 at = wbase[kk] + cnt[kk] + __popc(ballot & ((1u << lane) - 1u));
                         L.data[at] = value;
                         L.indices[at] = rpos;
+                        if (L.idx16)
+                        {
+                            L.idx16[at] = (unsigned short)rpos;
+                            L.dat8[at] = (signed char)value;
+                        }
                     }
                     cnt[kk] += __popc(ballot);
                 }

@@ -15,15 +15,22 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <random>
 #include <string>
 #include <vector>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <immintrin.h>
 
 using namespace tb;
 
@@ -221,6 +228,9 @@ struct PrimeState {
     std::vector<uint32_t> base;   // [N][3] RNG-exact base points of all representatives (lazy)
 };
 
+struct Copier;
+static void copier_destroy(Copier *c);
+
 struct tb_genus {
     int N = 0, K = 0;
     uint64_t seed = 0;
@@ -247,6 +257,11 @@ struct tb_genus {
     DevBuf<int> d_tab;          // rowbase | rowfirst | rowcount   (row kernels)
     DevBuf<i64> d_nnz;          // nnz | nnzbase
     DevBuf<u64> d_lookback;     // [2^K][rows] look-back words + ticket (fused row kernel)
+    DevBuf<int> d_maxmult;      // [1] largest |entry| bound of the last T_p (narrow read-back)
+    int *h_maxmult = nullptr;   // pinned [1]
+    struct Copier *copier = nullptr;   // background thread of the narrow read-back (started on first use)
+    bool allow_narrow = true;     // TBIRCH_NO_NARROW_COPY turns the compressed read-back off
+    int64_t narrow_min_nnz = 1 << 18;   // smaller matrices are copied as they are (TBIRCH_NARROW_MIN_NNZ)
     bool allow_fused = true;
     bool force_checked = false;   // TBIRCH_FORCE_CHECKED: always run the checked C128 kernel in precise mode
     int last_int_mode = -1;       // tb_last_int_mode
@@ -275,9 +290,18 @@ struct tb_hecke {
     tb_genus *g = nullptr;
     int C = 0;
     int rep_begin = 0, rep_end = 0;
+    int maxmult = 0x7fffffff;       // bound on |entry| (largest number of neighbors of a row in one class)
     std::vector<int> rows, rowfirst, rowbase;
     std::vector<int64_t> nnz, nnzbase;
     PoolBuf<int> d_indptr, d_data, d_indices;
+    PoolBuf<unsigned short> d_idx16;   // narrow twins of d_indices / d_data written by the row kernel:
+    PoolBuf<signed char> d_dat8;       //   3 bytes per entry for the read-back over PCIe
+    // asynchronous host read-backs still in flight (tb_hecke_copy_wait)
+    std::mutex copy_mx;
+    std::condition_variable copy_cv;
+    int copy_pending = 0;
+    cudaEvent_t copy_ev = nullptr;     // last plain cudaMemcpyAsync of an asynchronous copy
+    bool copy_ev_armed = false;
 };
 
 struct tb_isoseq {
@@ -449,11 +473,18 @@ extern "C" int tb_genus_create(const tb_genus_desc *d, tb_genus **out)
     g->allow_fused = getenv("TBIRCH_TWO_PASS_ROWS") == nullptr;   // debugging / A-B switches
     g->force_checked = getenv("TBIRCH_FORCE_CHECKED") != nullptr;
     g->force_wide = getenv("TBIRCH_FORCE_WIDE") != nullptr;
+    g->allow_narrow = getenv("TBIRCH_NO_NARROW_COPY") == nullptr;
+    // several ranks sharing one host saturate its memory system with widening traffic sooner than with
+    // plain DMA: keep the narrow read-back for one or two processes per host
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) if (atoi(e) > 2 && !getenv("TBIRCH_FORCE_NARROW_COPY")) g->allow_narrow = false;
+    if (const char *e = getenv("TBIRCH_NARROW_MIN_NNZ")) g->narrow_min_nnz = std::max(1ll, atoll(e));
     TB_CUDA(g->d_err.reserve(2));
     TB_CUDA(g->d_tab.reserve(3 * (size_t)C));
     TB_CUDA(g->d_nnz.reserve(2 * (size_t)C));
     TB_CUDA(cudaMallocHost((void **)&g->h_err, 2 * sizeof(u64)));
     TB_CUDA(cudaMallocHost((void **)&g->h_nnz, 2 * (size_t)C * sizeof(i64)));
+    TB_CUDA(g->d_maxmult.reserve(1));
+    TB_CUDA(cudaMallocHost((void **)&g->h_maxmult, sizeof(int)));
     TB_CUDA(cudaMallocHost((void **)&g->h_tab, 3 * (size_t)C * sizeof(int)));
     {
         int dev = 0;
@@ -492,6 +523,10 @@ extern "C" void tb_genus_destroy(tb_genus *g)
     for (int i = 0; i < 2; ++i) { if (g->h_stage[i]) cudaFreeHost(g->h_stage[i]); if (g->ev_stage[i]) cudaEventDestroy(g->ev_stage[i]); }
     if (g->h_err) cudaFreeHost(g->h_err);
     if (g->h_nnz) cudaFreeHost(g->h_nnz);
+    if (g->h_maxmult) cudaFreeHost(g->h_maxmult);
+    g->d_maxmult.release();
+    copier_destroy(g->copier);
+    g->copier = nullptr;
     if (g->h_tab) cudaFreeHost(g->h_tab);
     if (g->h_table) cudaFreeHost(g->h_table);
     if (g->h_base) cudaFreeHost(g->h_base);
@@ -821,6 +856,12 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     }
     const size_t total_b = g->device_bytes;
     const bool fused = g->allow_fused && (size_t)cap_total * 8 <= std::min<size_t>((size_t)48 << 30, total_b / 3);
+    // The row kernel also writes uint16 / int8 twins of indices / data when a host read-back could use
+    // them: columns fit 16 bits, the matrices are large, and ~(p+1)/N neighbors per class keeps entries in 8 bits.
+    int64_t max_dim = 0;
+    for (int k = 0; k < C; ++k) max_dim = std::max<int64_t>(max_dim, g->dims[k]);
+    const bool narrow_possible = g->allow_narrow && max_dim <= 65536 && cap_total >= g->narrow_min_nnz &&
+                                 (P1 <= 127 || (int64_t)P1 <= 32 * (int64_t)N);
 
     RowLaunch R;
     memset(&R, 0, sizeof(R));
@@ -830,6 +871,8 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     R.indptr_all = h->d_indptr.ptr;
     R.nnzbase = d_nnz.ptr + C;
     R.nnz_out = d_nnz.ptr;
+    R.maxmult = g->d_maxmult.ptr;
+    TB_CUDA(cudaMemsetAsync(g->d_maxmult.ptr, 0, sizeof(int), g->stream));
     const size_t smem = rows_smem_bytes(N, P1);
     if (smem > 218 * 1024)
         return fail(TB_ERR_RUNTIME, "libtbirch: row accumulation needs more shared memory than one SM has for this (N, p)");
@@ -854,9 +897,15 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     if (fused)
     {
         int64_t off = 0;
-        for (int k = 0; k < C; ++k) { h->nnzbase[k] = off; g->h_nnz[C + k] = off; off += cap[k]; }
-        TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(cap_total, 1), g->stream));
-        TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(cap_total, 1), g->stream));
+        for (int k = 0; k < C; ++k) { h->nnzbase[k] = off; g->h_nnz[C + k] = off; off += (cap[k] + 3) & ~(int64_t)3; }
+        TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(off, 1), g->stream));
+        TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(off, 1), g->stream));
+        if (narrow_possible)
+        {
+            TB_CUDA(h->d_idx16.reserve((size_t)std::max<int64_t>(off, 1), g->stream));
+            TB_CUDA(h->d_dat8.reserve((size_t)std::max<int64_t>(off, 1), g->stream));
+            R.idx16 = h->d_idx16.ptr; R.dat8 = h->d_dat8.ptr;
+        }
         TB_CUDA(g->d_lookback.reserve((size_t)C * rows + 2));
         TB_CUDA(cudaMemsetAsync(g->d_lookback.ptr, 0, ((size_t)C * rows + 2) * sizeof(u64), g->stream));
         TB_CUDA(cudaMemcpyAsync(d_nnz.ptr + C, g->h_nnz + C, C * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
@@ -869,9 +918,11 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
         TB_CUDA(cudaEventRecord(g->ev2, g->stream));
         TB_CUDA(cudaMemcpyAsync(g->h_err, g->d_err.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, g->stream));
         TB_CUDA(cudaMemcpyAsync(g->h_nnz, d_nnz.ptr, C * sizeof(i64), cudaMemcpyDeviceToHost, g->stream));
+        TB_CUDA(cudaMemcpyAsync(g->h_maxmult, g->d_maxmult.ptr, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
         TB_CUDA(cudaStreamSynchronize(g->stream));
         if (int rc = check_errors(g)) { return rc; }
         for (int k = 0; k < C; ++k) h->nnz[k] = g->h_nnz[k];
+        h->maxmult = *g->h_maxmult;
     }
     else
     {
@@ -884,14 +935,22 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
 
         TB_CUDA(cudaMemcpyAsync(g->h_err, g->d_err.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, g->stream));
         TB_CUDA(cudaMemcpyAsync(g->h_nnz, d_nnz.ptr, C * sizeof(i64), cudaMemcpyDeviceToHost, g->stream));
+        TB_CUDA(cudaMemcpyAsync(g->h_maxmult, g->d_maxmult.ptr, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
         TB_CUDA(cudaStreamSynchronize(g->stream));
         if (int rc = check_errors(g)) { return rc; }
         for (int k = 0; k < C; ++k) h->nnz[k] = g->h_nnz[k];
+        h->maxmult = *g->h_maxmult;
 
         int64_t total_nnz = 0;
         for (int k = 0; k < C; ++k) { h->nnzbase[k] = total_nnz; total_nnz += h->nnz[k]; }
         TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(total_nnz, 1), g->stream));
         TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(total_nnz, 1), g->stream));
+        if (narrow_possible)
+        {
+            TB_CUDA(h->d_idx16.reserve((size_t)std::max<int64_t>(total_nnz, 1), g->stream));
+            TB_CUDA(h->d_dat8.reserve((size_t)std::max<int64_t>(total_nnz, 1), g->stream));
+            R.idx16 = h->d_idx16.ptr; R.dat8 = h->d_dat8.ptr;
+        }
         for (int k = 0; k < C; ++k) g->h_nnz[C + k] = h->nnzbase[k];
         TB_CUDA(cudaMemcpyAsync(d_nnz.ptr + C, g->h_nnz + C, C * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
         R.data = h->d_data.ptr; R.indices = h->d_indices.ptr;
@@ -965,15 +1024,327 @@ static int copy_out(tb_genus *g, void *dst, const void *src_dev, size_t bytes)
     return TB_OK;
 }
 
-extern "C" int tb_hecke_copy_sparse(tb_hecke *h, int64_t k, int32_t *data, int32_t *indices, int32_t *indptr)
+// ---------------------------------------------------------------------------
+// Narrow read-back.  A T_p at the bench size is 3.6 GB of int32 CSR; PCIe moves it at
+// ~54 GB/s, three times longer than the GPU needs to compute it.  When every column index
+// fits 16 bits and every |entry| fits 8 (known from the row kernel's max-multiplicity word),
+// the device packs indices/entries to 3 bytes per entry, the DMA moves those into pinned
+// staging, and host threads widen them into the caller's int32 arrays with streaming stores.
+// Two internal streams alternate chunks so the DMA of one chunk overlaps the widening of
+// the previous one; the caller's stream waits on both.
+// ---------------------------------------------------------------------------
+static const size_t TB_NARROW_CHUNK = (size_t)16 << 20;      // entries per chunk (48 MB of staging)
+
+__attribute__((target("avx2"))) static void widen_u16_avx2(const unsigned short *src, int32_t *dst, size_t n)
 {
-    if (!h || k < 0 || k >= h->C) return fail(TB_ERR_INVALID_ARGUMENT, "tb_hecke_copy_sparse: bad conductor index");
-    cudaStream_t st = h->g->stream;
-    const size_t nnz = (size_t)h->nnz[k];
-    if (nnz && data) if (int rc = copy_out(h->g, data, h->d_data.ptr + h->nnzbase[k], nnz * sizeof(int))) return rc;
-    if (nnz && indices) if (int rc = copy_out(h->g, indices, h->d_indices.ptr + h->nnzbase[k], nnz * sizeof(int))) return rc;
-    if (indptr) if (int rc = copy_out(h->g, indptr, h->d_indptr.ptr + h->rowbase[k], ((size_t)h->rows[k] + 1) * sizeof(int))) return rc;
-    TB_CUDA(cudaStreamSynchronize(st));
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 31)) { dst[i] = src[i]; ++i; }
+    for (; i + 8 <= n; i += 8)
+        _mm256_stream_si256((__m256i *)(dst + i), _mm256_cvtepu16_epi32(_mm_loadu_si128((const __m128i *)(src + i))));
+    for (; i < n; ++i) dst[i] = src[i];
+    _mm_sfence();
+}
+__attribute__((target("avx2"))) static void widen_i8_avx2(const signed char *src, int32_t *dst, size_t n)
+{
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 31)) { dst[i] = src[i]; ++i; }
+    for (; i + 8 <= n; i += 8)
+        _mm256_stream_si256((__m256i *)(dst + i), _mm256_cvtepi8_epi32(_mm_loadl_epi64((const __m128i *)(src + i))));
+    for (; i < n; ++i) dst[i] = src[i];
+    _mm_sfence();
+}
+static void widen_u16(const unsigned short *src, int32_t *dst, size_t n)
+{
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) { widen_u16_avx2(src, dst, n); return; }
+    for (size_t i = 0; i < n; ++i) dst[i] = src[i];
+}
+static void widen_i8(const signed char *src, int32_t *dst, size_t n)
+{
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) { widen_i8_avx2(src, dst, n); return; }
+    for (size_t i = 0; i < n; ++i) dst[i] = src[i];
+}
+
+// A small process-wide pool: parallel_for over [0, n) in `parts` slices.
+class HostPool {
+public:
+    static HostPool &get() { static HostPool p; return p; }
+    int size() const { return (int)workers.size() + 1; }
+    template <class F>
+    void run(int parts, F fn)
+    {
+        std::function<void(int)> f = fn;
+        std::unique_lock<std::mutex> user(user_mx);          // one parallel region at a time
+        {
+            std::lock_guard<std::mutex> lk(mx);
+            job = &f; next = 0; total = parts; pending = parts; ++epoch;
+        }
+        cv.notify_all();
+        work();                                              // the calling thread takes slices too
+        std::unique_lock<std::mutex> lk(mx);
+        done_cv.wait(lk, [&] { return pending == 0; });
+        job = nullptr;
+    }
+private:
+    HostPool()
+    {
+        int n = 0;
+        if (const char *e = getenv("TBIRCH_HOST_THREADS")) n = atoi(e);
+        if (n <= 0)
+        {
+            int hw = (int)std::thread::hardware_concurrency();
+            int local = 1;
+            if (const char *e = getenv("LOCAL_WORLD_SIZE")) local = std::max(1, atoi(e));
+            n = std::max(2, std::min(8, hw / (2 * local)));
+        }
+        for (int i = 1; i < n; ++i) workers.emplace_back([this] { loop(); });
+    }
+    ~HostPool()
+    {
+        { std::lock_guard<std::mutex> lk(mx); stop = true; }
+        cv.notify_all();
+        for (auto &t : workers) t.join();
+    }
+    void work()
+    {
+        for (;;)
+        {
+            int i;
+            {
+                std::lock_guard<std::mutex> lk(mx);
+                if (!job || next >= total) return;
+                i = next++;
+            }
+            (*job)(i);
+            std::lock_guard<std::mutex> lk(mx);
+            if (--pending == 0) done_cv.notify_all();
+        }
+    }
+    void loop()
+    {
+        uint64_t seen = 0;
+        for (;;)
+        {
+            {
+                std::unique_lock<std::mutex> lk(mx);
+                cv.wait(lk, [&] { return stop || epoch != seen; });
+                if (stop) return;
+                seen = epoch;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> workers;
+    std::mutex mx, user_mx;
+    std::condition_variable cv, done_cv;
+    std::function<void(int)> *job = nullptr;
+    int next = 0, total = 0, pending = 0;
+    uint64_t epoch = 0;
+    bool stop = false;
+};
+
+struct WidenJob {
+    const unsigned short *idx16;
+    const signed char *dat8;
+    int32_t *indices, *data;
+    size_t n;
+};
+
+static void widen_run(const WidenJob &job)
+{
+    const WidenJob *j = &job;
+    const size_t slice = ((size_t)1 << 18);
+    const int parts = (int)((j->n + slice - 1) / slice);
+    HostPool::get().run(parts, [j, slice](int i) {
+        const size_t lo = (size_t)i * slice, len = std::min(slice, j->n - lo);
+        if (j->indices) widen_u16(j->idx16 + lo, j->indices + lo, len);
+        if (j->data) widen_i8(j->dat8 + lo, j->data + lo, len);
+    });
+}
+
+static bool host_pointer(const void *p)
+{
+    if (!p) return true;
+    cudaPointerAttributes attr;
+    const bool known = cudaPointerGetAttributes(&attr, p) == cudaSuccess;
+    cudaGetLastError();
+    return !known || attr.type == cudaMemoryTypeUnregistered || attr.type == cudaMemoryTypeHost;
+}
+
+// One background thread per genus drives the narrow read-back: it keeps two chunk DMAs in
+// flight on its own stream (three pinned staging slots) and widens each chunk as its DMA
+// lands, so the copy engine and the host threads work concurrently and the caller's thread
+// is free to launch the next T_p.  (Host functions enqueued in CUDA streams serialised the
+// DMA with the widening; a plain thread that waits on events does not.)
+struct CopyRequest {
+    tb_hecke *h;
+    const unsigned short *d_idx;
+    const signed char *d_dat;
+    int32_t *indices, *data;
+    size_t nnz;
+};
+
+struct Copier {
+    static const int SLOTS = 3;
+    int device = 0;
+    std::thread th;
+    std::mutex mx;
+    std::condition_variable cv;
+    std::deque<CopyRequest> q;
+    bool stop = false;
+    std::string error;
+    cudaStream_t stream = nullptr;
+    char *stage[SLOTS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[SLOTS] = {nullptr, nullptr, nullptr};
+
+    struct Chunk { CopyRequest req; size_t off, len; int slot; bool last; };
+
+    void body()
+    {
+        cudaSetDevice(device);
+        std::deque<Chunk> flight;
+        CopyRequest cur;
+        size_t cur_off = 0;
+        bool have = false;
+        uint64_t issued = 0;
+        for (;;)
+        {
+            while (flight.size() < 2 && fill_one(flight, cur, cur_off, have, issued)) {}
+            if (flight.empty())
+            {
+                std::unique_lock<std::mutex> lk(mx);
+                cv.wait(lk, [&] { return stop || !q.empty(); });
+                if (stop && q.empty()) return;
+                continue;
+            }
+            const Chunk c = flight.front();
+            flight.pop_front();
+            const cudaError_t e = cudaEventSynchronize(ev[c.slot]);
+            if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(mx); error = cudaGetErrorString(e); }
+            // issue the next DMA before widening this chunk: its slot (issue order modulo 3) is neither
+            // this chunk's nor the one still in flight, and its previous user was widened an iteration ago
+            fill_one(flight, cur, cur_off, have, issued);
+            const WidenJob job{(const unsigned short *)stage[c.slot], (const signed char *)(stage[c.slot] + TB_NARROW_CHUNK * 2),
+                               c.req.indices ? c.req.indices + c.off : nullptr, c.req.data ? c.req.data + c.off : nullptr, c.len};
+            widen_run(job);
+            if (c.last)
+            {
+                std::lock_guard<std::mutex> lk(c.req.h->copy_mx);
+                --c.req.h->copy_pending;
+                c.req.h->copy_cv.notify_all();
+            }
+        }
+    }
+    bool fill_one(std::deque<Chunk> &flight, CopyRequest &cur, size_t &cur_off, bool &have, uint64_t &issued)
+    {
+        if (!have)
+        {
+            std::lock_guard<std::mutex> lk(mx);
+            if (q.empty()) return false;
+            cur = q.front();
+            q.pop_front();
+            cur_off = 0;
+            have = true;
+        }
+        Chunk c;
+        c.req = cur;
+        c.off = cur_off;
+        c.len = std::min(TB_NARROW_CHUNK, cur.nnz - cur_off);
+        c.slot = (int)(issued++ % SLOTS);
+        cur_off += c.len;
+        c.last = cur_off >= cur.nnz;
+        if (c.last) have = false;
+        unsigned short *s_idx = (unsigned short *)stage[c.slot];
+        signed char *s_dat = (signed char *)(stage[c.slot] + TB_NARROW_CHUNK * 2);
+        cudaError_t e = cudaSuccess;
+        if (cur.indices) e = cudaMemcpyAsync(s_idx, cur.d_idx + c.off, c.len * 2, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess && cur.data) e = cudaMemcpyAsync(s_dat, cur.d_dat + c.off, c.len, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[c.slot], stream);
+        if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(mx); error = cudaGetErrorString(e); }
+        flight.push_back(c);
+        return true;
+    }
+};
+
+static void copier_destroy(Copier *c)
+{
+    if (!c) return;
+    {
+        std::lock_guard<std::mutex> lk(c->mx);
+        c->stop = true;
+    }
+    c->cv.notify_all();
+    if (c->th.joinable()) c->th.join();
+    for (int i = 0; i < Copier::SLOTS; ++i)
+    {
+        if (c->stage[i]) cudaFreeHost(c->stage[i]);
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static bool narrow_applies(const tb_hecke *h, int64_t k, const int32_t *data, const int32_t *indices)
+{
+    return h->d_idx16.ptr && h->maxmult <= 127 && h->nnz[k] >= h->g->narrow_min_nnz &&
+           (data || indices) && host_pointer(data) && host_pointer(indices);
+}
+
+// data / indices of conductor k -> host arrays through the 3-byte format.  Returns at once;
+// tb_hecke_copy_wait (or the synchronous tb_hecke_copy_sparse) observes completion.
+static int narrow_copy(tb_hecke *h, int64_t k, int32_t *data, int32_t *indices)
+{
+    tb_genus *g = h->g;
+    if (!g->copier)
+    {
+        std::unique_ptr<Copier> c(new Copier);
+        TB_CUDA(cudaGetDevice(&c->device));
+        TB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (int i = 0; i < Copier::SLOTS; ++i)
+        {
+            TB_CUDA(cudaMallocHost((void **)&c->stage[i], TB_NARROW_CHUNK * 3));
+            TB_CUDA(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
+        }
+        Copier *raw = c.release();
+        raw->th = std::thread([raw] { raw->body(); });
+        g->copier = raw;
+    }
+    CopyRequest r{h, h->d_idx16.ptr + h->nnzbase[k], h->d_dat8.ptr + h->nnzbase[k], indices, data, (size_t)h->nnz[k]};
+    {
+        std::lock_guard<std::mutex> lk(h->copy_mx);
+        ++h->copy_pending;
+    }
+    {
+        std::lock_guard<std::mutex> lk(g->copier->mx);
+        g->copier->q.push_back(r);
+    }
+    g->copier->cv.notify_all();
+    return TB_OK;
+}
+
+extern "C" int tb_hecke_copy_wait(tb_hecke *h)
+{
+    if (!h) return fail(TB_ERR_INVALID_ARGUMENT, "tb_hecke_copy_wait: null argument");
+    {
+        std::unique_lock<std::mutex> lk(h->copy_mx);
+        h->copy_cv.wait(lk, [&] { return h->copy_pending == 0; });
+    }
+    if (h->copy_ev_armed)
+    {
+        TB_CUDA(cudaEventSynchronize(h->copy_ev));
+        h->copy_ev_armed = false;
+    }
+    if (h->g->copier)
+    {
+        std::lock_guard<std::mutex> lk(h->g->copier->mx);
+        if (!h->g->copier->error.empty())
+        {
+            const std::string msg = "libtbirch: read-back failed: " + h->g->copier->error;
+            h->g->copier->error.clear();
+            return fail(TB_ERR_RUNTIME, msg);
+        }
+    }
     return TB_OK;
 }
 
@@ -983,10 +1354,78 @@ extern "C" int tb_hecke_copy_sparse_async(tb_hecke *h, int64_t k, int32_t *data,
     if (!h || k < 0 || k >= h->C) return fail(TB_ERR_INVALID_ARGUMENT, "tb_hecke_copy_sparse_async: bad conductor index");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const size_t nnz = (size_t)h->nnz[k];
-    if (nnz && data) TB_CUDA(cudaMemcpyAsync(data, h->d_data.ptr + h->nnzbase[k], nnz * sizeof(int), cudaMemcpyDefault, st));
-    if (nnz && indices) TB_CUDA(cudaMemcpyAsync(indices, h->d_indices.ptr + h->nnzbase[k], nnz * sizeof(int), cudaMemcpyDefault, st));
+    if (nnz && narrow_applies(h, k, data, indices))
+    {
+        if (int rc = narrow_copy(h, k, data, indices)) return rc;
+    }
+    else
+    {
+        if (nnz && data) TB_CUDA(cudaMemcpyAsync(data, h->d_data.ptr + h->nnzbase[k], nnz * sizeof(int), cudaMemcpyDefault, st));
+        if (nnz && indices) TB_CUDA(cudaMemcpyAsync(indices, h->d_indices.ptr + h->nnzbase[k], nnz * sizeof(int), cudaMemcpyDefault, st));
+    }
     if (indptr) TB_CUDA(cudaMemcpyAsync(indptr, h->d_indptr.ptr + h->rowbase[k], ((size_t)h->rows[k] + 1) * sizeof(int), cudaMemcpyDefault, st));
+    if (!h->copy_ev) TB_CUDA(cudaEventCreateWithFlags(&h->copy_ev, cudaEventDisableTiming));
+    TB_CUDA(cudaEventRecord(h->copy_ev, st));
+    h->copy_ev_armed = true;
     return TB_OK;
+}
+
+extern "C" int tb_hecke_copy_sparse(tb_hecke *h, int64_t k, int32_t *data, int32_t *indices, int32_t *indptr)
+{
+    if (!h || k < 0 || k >= h->C) return fail(TB_ERR_INVALID_ARGUMENT, "tb_hecke_copy_sparse: bad conductor index");
+    cudaStream_t st = h->g->stream;
+    const size_t nnz = (size_t)h->nnz[k];
+    if (nnz && narrow_applies(h, k, data, indices))
+    {
+        if (int rc = narrow_copy(h, k, data, indices)) return rc;
+    }
+    else
+    {
+        if (nnz && data) if (int rc = copy_out(h->g, data, h->d_data.ptr + h->nnzbase[k], nnz * sizeof(int))) return rc;
+        if (nnz && indices) if (int rc = copy_out(h->g, indices, h->d_indices.ptr + h->nnzbase[k], nnz * sizeof(int))) return rc;
+    }
+    if (indptr) if (int rc = copy_out(h->g, indptr, h->d_indptr.ptr + h->rowbase[k], ((size_t)h->rows[k] + 1) * sizeof(int))) return rc;
+    TB_CUDA(cudaStreamSynchronize(st));
+    return tb_hecke_copy_wait(h);
+}
+
+/* Host-side widening throughput of this machine (no GPU involved): widens `entries` packed
+ * entries with the library's thread pool, returns output GB/s, the pool size and whether the
+ * AVX2 streaming-store path is in use. */
+extern "C" int tb_host_widen_probe(int64_t entries, double *out_gbps, int *threads, int *avx2)
+{
+    if (entries <= 0) return fail(TB_ERR_INVALID_ARGUMENT, "tb_host_widen_probe: bad size");
+    std::vector<unsigned short> idx((size_t)entries, 7);
+    std::vector<signed char> dat((size_t)entries, -3);
+    int32_t *oi = (int32_t *)aligned_alloc(64, (size_t)entries * 4), *od = (int32_t *)aligned_alloc(64, (size_t)entries * 4);
+    if (!oi || !od) return fail(TB_ERR_RUNTIME, "tb_host_widen_probe: out of memory");
+    memset(oi, 0, (size_t)entries * 4);
+    memset(od, 0, (size_t)entries * 4);
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep)
+    {
+        const WidenJob job{idx.data(), dat.data(), oi, od, (size_t)entries};
+        const auto t0 = std::chrono::steady_clock::now();
+        widen_run(job);
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        best = std::max(best, (double)entries * 8.0 / sec / 1e9);
+    }
+    const bool ok = oi[entries - 1] == 7 && od[entries - 1] == -3 && oi[0] == 7 && od[0] == -3;
+    free(oi);
+    free(od);
+    if (!ok) return fail(TB_ERR_RUNTIME, "tb_host_widen_probe: wrong result");
+    if (out_gbps) *out_gbps = best;
+    if (threads) *threads = HostPool::get().size();
+    if (avx2) *avx2 = __builtin_cpu_supports("avx2") ? 1 : 0;
+    return TB_OK;
+}
+
+/* Bytes that cross PCIe for data + indices of conductor k on a host read-back (diagnostic). */
+extern "C" int64_t tb_hecke_transfer_bytes(const tb_hecke *h, int64_t k)
+{
+    if (!h || k < 0 || k >= h->C) return 0;
+    const bool narrow = h->d_idx16.ptr && h->maxmult <= 127 && h->nnz[k] >= h->g->narrow_min_nnz;
+    return h->nnz[k] * (narrow ? 3 : 8) + ((int64_t)h->rows[k] + 1) * 4;
 }
 
 extern "C" int tb_hecke_copy_dense(tb_hecke *h, int64_t k, int32_t *matrix)
@@ -1025,7 +1464,9 @@ extern "C" int tb_hecke_copy_dense(tb_hecke *h, int64_t k, int32_t *matrix)
 extern "C" void tb_hecke_destroy(tb_hecke *h)
 {
     if (!h) return;
-    h->d_indptr.release(); h->d_data.release(); h->d_indices.release();
+    tb_hecke_copy_wait(h);                       // an asynchronous read-back may still be reading the device arrays
+    if (h->copy_ev) cudaEventDestroy(h->copy_ev);
+    h->d_indptr.release(); h->d_data.release(); h->d_indices.release(); h->d_idx16.release(); h->d_dat8.release();
     delete h;
 }
 

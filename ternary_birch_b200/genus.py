@@ -286,6 +286,14 @@ class HeckeResult:
     def row_begin(self, k) -> int:
         return int(cabi.lib().tb_hecke_row_begin(self._h, k))
 
+    def wait_copies(self) -> None:
+        """Block until every copy_sparse_to_async issued on this result has landed in its destination."""
+        cabi.check(cabi.lib().tb_hecke_copy_wait(self._h))
+
+    def transfer_bytes(self, k) -> int:
+        """Bytes a host read-back of conductor k moves over PCIe (narrow 3-byte entries when they apply)."""
+        return int(cabi.lib().tb_hecke_transfer_bytes(self._h, int(k)))
+
     def total_nnz(self) -> int:
         return sum(self.shape(k)[2] for k in range(self.num_conductors()))
 

@@ -323,3 +323,49 @@ def test_precise_kernel_variants_agree(tables, port_oracle, monkeypatch, name, p
     if small:
         assert np.array_equal(got[None][1], oracle.neighbor_records(p, True)[:rows])
         assert np.array_equal(got[None][2], oracle.isometry_sequence(p, True))
+
+
+@pytest.mark.parametrize("name,p,want_narrow", [("85085", 997, True), ("85085", 65521, False), ("1062347", 1009, True),
+                                                 ("1009091", 107, True)])
+def test_narrow_readback_matches_plain(tables, monkeypatch, name, p, want_narrow):
+    """Host read-backs of large matrices travel as uint16 columns + int8 entries and are widened by
+    host threads; the arrays must equal the plain int32 copy, into pageable and into pinned memory,
+    and the plain path must be taken when an entry does not fit 8 bits (level 85085, p = 65521:
+    ~500 neighbors per class)."""
+    import torch
+    from ternary_birch_b200 import Genus
+    t = tables(name)
+    got = {}
+    for narrow in (False, True):
+        monkeypatch.delenv("TBIRCH_NO_NARROW_COPY", raising=False)
+        monkeypatch.setenv("TBIRCH_NARROW_MIN_NNZ", "1")
+        if not narrow:
+            monkeypatch.setenv("TBIRCH_NO_NARROW_COPY", "1")
+        g = Genus(t, precise=True)
+        try:
+            res = g.hecke_device(p)
+            rows, dim, nnz = res.shape(0)
+            used = res.transfer_bytes(0) < 8 * nnz + 4 * (rows + 1)
+            assert used == (narrow and want_narrow)
+            got[narrow] = {k: res.sparse(k) for k in range(res.num_conductors())}
+            if narrow:
+                # asynchronous variant into pinned memory on a side stream
+                side = torch.cuda.Stream()
+                for k in (0, res.num_conductors() - 1):
+                    rows, dim, nnz = res.shape(k)
+                    d = torch.full((max(nnz, 1),), -7, dtype=torch.int32).pin_memory()
+                    i = torch.full((max(nnz, 1),), -7, dtype=torch.int32).pin_memory()
+                    ptr = torch.zeros(rows + 1, dtype=torch.int32).pin_memory()
+                    torch.cuda.synchronize()
+                    res.copy_sparse_to_async(k, d.data_ptr(), i.data_ptr(), ptr.data_ptr(), side.cuda_stream)
+                    side.synchronize()
+                    res.wait_copies()
+                    assert np.array_equal(d.numpy()[:nnz], got[True][k][0])
+                    assert np.array_equal(i.numpy()[:nnz], got[True][k][1])
+                    assert np.array_equal(ptr.numpy(), got[True][k][2])
+            res.close()
+        finally:
+            g.close()
+    for k in got[False]:
+        for a, b in zip(got[False][k], got[True][k]):
+            assert np.array_equal(a, b), k
