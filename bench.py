@@ -334,17 +334,24 @@ def main():
         ev.record(copy_stream)
         pending[slot] = (res, ev)
 
-    step_e2e(0)
+    # warm-up: W untimed steps, at least two so that both pinned result sets have been written by the
+    # host once (the first CPU store to a page of a fresh cudaHostAlloc mapping takes a minor fault)
+    for i in range(max(2, args.warmup)):
+        step_e2e(i)
     drain(0)
+    drain(1)
     sync_all()
     e_start = torch.cuda.Event(enable_timing=True)
     e_stop = torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
     e_start.record(stream)
+    step_marks = [wall0]
     for i in range(args.steps):
         step_e2e(i)
+        step_marks.append(time.perf_counter())
     drain(0)
     drain(1)
+    step_marks.append(time.perf_counter())
     e_stop.record(stream)
     sync_all()
     wall_e2e = time.perf_counter() - wall0
@@ -420,6 +427,7 @@ def main():
                     roofline=roofline, cpu_baseline=cpu,
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
                              result_bytes_per_step=result_bytes,
+                             step_wall_ms=[round((b - a) * 1e3, 1) for a, b in zip(step_marks, step_marks[1:])],
                              readback="uint16 column + int8 entry over PCIe, widened to the reference's int32 CSR by host threads" if d2h_bytes < result_bytes else "int32 CSR over PCIe"),
                     gpu_launches=int(launches_timed), clocks=clocks, numa_node=numa_node, T_p_wall_ms=total_ms / args.steps,
                     final_gather_ms=gather_ms)

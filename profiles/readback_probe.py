@@ -27,7 +27,8 @@ for narrow in (False, True):
                      torch.empty(rows + 1, dtype=torch.int32).pin_memory()))
     side = torch.cuda.Stream()
     best = 1e9
-    for rep in range(4):
+    times = []
+    for rep in range(int(os.environ.get('REPS', 4))):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for k in range(C):
@@ -35,10 +36,12 @@ for narrow in (False, True):
             res.copy_sparse_to_async(k, d.data_ptr(), i.data_ptr(), ptr.data_ptr(), side.cuda_stream)
         side.synchronize()
         res.wait_copies()
-        best = min(best, (time.perf_counter() - t0) * 1e3)
+        times.append((time.perf_counter() - t0) * 1e3)
+        best = min(best, times[-1])
     pcie = sum(res.transfer_bytes(k) for k in range(C))
     total = sum(8 * res.shape(k)[2] + 4 * (res.shape(k)[0] + 1) for k in range(C))
     print(f"narrow={narrow} threads={os.environ.get('TBIRCH_HOST_THREADS', 'default')}: {best:.1f} ms, "
-          f"{pcie / 1e9:.2f} GB over PCIe, {total / 1e9:.2f} GB delivered = {total / best / 1e6:.1f} GB/s")
+          f"{pcie / 1e9:.2f} GB over PCIe, {total / 1e9:.2f} GB delivered = {total / best / 1e6:.1f} GB/s; all reps: "
+          + " ".join(f"{t:.0f}" for t in times))
     res.close()
     g.close()

@@ -31,6 +31,9 @@
 #include <mutex>
 #include <thread>
 #include <immintrin.h>
+#include <sys/resource.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 using namespace tb;
 
@@ -1123,6 +1126,8 @@ private:
     }
     void loop()
     {
+        // widening is bulk work: let the thread that launches kernels (and CUDA's own threads) preempt it
+        setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), 10);
         uint64_t seen = 0;
         for (;;)
         {
