@@ -1099,7 +1099,7 @@ private:
             int hw = (int)std::thread::hardware_concurrency();
             int local = 1;
             if (const char *e = getenv("LOCAL_WORLD_SIZE")) local = std::max(1, atoi(e));
-            n = std::max(2, std::min(8, hw / (2 * local)));
+            n = std::max(2, std::min(32, hw / local));     // workers are niced: the launching thread preempts them
         }
         for (int i = 1; i < n; ++i) workers.emplace_back([this] { loop(); });
     }
