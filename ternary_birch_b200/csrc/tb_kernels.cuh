@@ -560,8 +560,11 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
                     if (pass == 1 && value != 0)
                     {
                         const i64 at = wbase[kk] + cnt[kk] + __popc(ballot & ((1u << lane) - 1u));
-                        L.data[at] = value;
-                        L.indices[at] = rpos;
+                        if (L.data)
+                        {
+                            L.data[at] = value;
+                            L.indices[at] = rpos;
+                        }
                         if (L.idx16)
                         {
                             L.idx16[at] = (unsigned short)rpos;
@@ -640,6 +643,17 @@ __global__ void indptr_scan_kernel(int *indptr_all, const int *rowbase, const in
         carry += total;
     }
     if (threadIdx.x == 0) { indptr[0] = 0; nnz[k] = carry; }
+}
+
+// int32 arrays from the narrow ones (device consumers of a result the row kernel wrote narrow only).
+__global__ void widen_device_kernel(const unsigned short *idx16, const signed char *dat8, size_t n, int *indices, int *data)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        indices[i] = (int)idx16[i];
+        data[i] = (int)dat8[i];
+    }
 }
 
 // Dense rows from the CSR rows of one conductor.

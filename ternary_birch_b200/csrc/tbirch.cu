@@ -297,6 +297,8 @@ struct tb_hecke {
     std::vector<int> rows, rowfirst, rowbase;
     std::vector<int64_t> nnz, nnzbase;
     PoolBuf<int> d_indptr, d_data, d_indices;
+    bool wide_valid = true;            // d_data / d_indices hold the result (else only the narrow twins do)
+    int64_t extent = 0;                // entries spanned by the per-conductor regions
     PoolBuf<unsigned short> d_idx16;   // narrow twins of d_indices / d_data written by the row kernel:
     PoolBuf<signed char> d_dat8;       //   3 bytes per entry for the read-back over PCIe
     // asynchronous host read-backs still in flight (tb_hecke_copy_wait)
@@ -901,20 +903,27 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     {
         int64_t off = 0;
         for (int k = 0; k < C; ++k) { h->nnzbase[k] = off; g->h_nnz[C + k] = off; off += (cap[k] + 3) & ~(int64_t)3; }
-        TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(off, 1), g->stream));
-        TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(off, 1), g->stream));
+        h->extent = off;
+        // when a narrow result is likely (columns fit 16 bits, ~(p+1)/N neighbors per class), write only
+        // that: 3 bytes per entry instead of 8; int32 arrays are made on demand (ensure_wide)
         if (narrow_possible)
         {
             TB_CUDA(h->d_idx16.reserve((size_t)std::max<int64_t>(off, 1), g->stream));
             TB_CUDA(h->d_dat8.reserve((size_t)std::max<int64_t>(off, 1), g->stream));
             R.idx16 = h->d_idx16.ptr; R.dat8 = h->d_dat8.ptr;
+            h->wide_valid = false;
+        }
+        else
+        {
+            TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(off, 1), g->stream));
+            TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(off, 1), g->stream));
+            R.data = h->d_data.ptr; R.indices = h->d_indices.ptr;
         }
         TB_CUDA(g->d_lookback.reserve((size_t)C * rows + 2));
         TB_CUDA(cudaMemsetAsync(g->d_lookback.ptr, 0, ((size_t)C * rows + 2) * sizeof(u64), g->stream));
         TB_CUDA(cudaMemcpyAsync(d_nnz.ptr + C, g->h_nnz + C, C * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
         R.lookback = g->d_lookback.ptr;
         R.ticket = (int *)(g->d_lookback.ptr + (size_t)C * rows);
-        R.data = h->d_data.ptr; R.indices = h->d_indices.ptr;
         rows_kernel<ROWS_FUSED><<<rows, threads, smem, g->stream>>>(R);
         ++g_launches;
         TB_CUDA(cudaGetLastError());
@@ -926,6 +935,22 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
         if (int rc = check_errors(g)) { return rc; }
         for (int k = 0; k < C; ++k) h->nnz[k] = g->h_nnz[k];
         h->maxmult = *g->h_maxmult;
+        if (!h->wide_valid && h->maxmult > 127)
+        {
+            // an entry does not fit 8 bits after all (few classes, large p): redo the row pass in int32
+            h->d_idx16.release(); h->d_dat8.release();
+            TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(off, 1), g->stream));
+            TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(off, 1), g->stream));
+            R.idx16 = nullptr; R.dat8 = nullptr;
+            R.data = h->d_data.ptr; R.indices = h->d_indices.ptr;
+            TB_CUDA(cudaMemsetAsync(g->d_lookback.ptr, 0, ((size_t)C * rows + 2) * sizeof(u64), g->stream));
+            rows_kernel<ROWS_FUSED><<<rows, threads, smem, g->stream>>>(R);
+            ++g_launches;
+            TB_CUDA(cudaGetLastError());
+            TB_CUDA(cudaEventRecord(g->ev2, g->stream));
+            TB_CUDA(cudaStreamSynchronize(g->stream));
+            h->wide_valid = true;
+        }
     }
     else
     {
@@ -946,17 +971,22 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
 
         int64_t total_nnz = 0;
         for (int k = 0; k < C; ++k) { h->nnzbase[k] = total_nnz; total_nnz += h->nnz[k]; }
-        TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(total_nnz, 1), g->stream));
-        TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(total_nnz, 1), g->stream));
-        if (narrow_possible)
+        h->extent = total_nnz;
+        if (narrow_possible && h->maxmult <= 127)            // the count pass already knows the largest entry
         {
             TB_CUDA(h->d_idx16.reserve((size_t)std::max<int64_t>(total_nnz, 1), g->stream));
             TB_CUDA(h->d_dat8.reserve((size_t)std::max<int64_t>(total_nnz, 1), g->stream));
             R.idx16 = h->d_idx16.ptr; R.dat8 = h->d_dat8.ptr;
+            h->wide_valid = false;
+        }
+        else
+        {
+            TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(total_nnz, 1), g->stream));
+            TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(total_nnz, 1), g->stream));
+            R.data = h->d_data.ptr; R.indices = h->d_indices.ptr;
         }
         for (int k = 0; k < C; ++k) g->h_nnz[C + k] = h->nnzbase[k];
         TB_CUDA(cudaMemcpyAsync(d_nnz.ptr + C, g->h_nnz + C, C * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
-        R.data = h->d_data.ptr; R.indices = h->d_indices.ptr;
         rows_kernel<ROWS_FILL><<<rows, threads, smem, g->stream>>>(R);
         ++g_launches;
         TB_CUDA(cudaGetLastError());
@@ -1290,6 +1320,29 @@ static void copier_destroy(Copier *c)
     delete c;
 }
 
+// int32 arrays for device consumers (device-pointer copies, dense rows, small matrices) of a result
+// that exists in narrow form only.
+static int ensure_wide(tb_hecke *h)
+{
+    if (h->wide_valid) return TB_OK;
+    cudaStream_t st = h->g->stream;
+    TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(h->extent, 1), st));
+    TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(h->extent, 1), st));
+    for (int k = 0; k < h->C; ++k)
+    {
+        const size_t n = (size_t)h->nnz[k];
+        if (!n) continue;
+        const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+        widen_device_kernel<<<blocks, 256, 0, st>>>(h->d_idx16.ptr + h->nnzbase[k], h->d_dat8.ptr + h->nnzbase[k], n,
+                                                    h->d_indices.ptr + h->nnzbase[k], h->d_data.ptr + h->nnzbase[k]);
+        ++g_launches;
+    }
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaStreamSynchronize(st));
+    h->wide_valid = true;
+    return TB_OK;
+}
+
 static bool narrow_applies(const tb_hecke *h, int64_t k, const int32_t *data, const int32_t *indices)
 {
     return h->d_idx16.ptr && h->maxmult <= 127 && h->nnz[k] >= h->g->narrow_min_nnz &&
@@ -1365,6 +1418,7 @@ extern "C" int tb_hecke_copy_sparse_async(tb_hecke *h, int64_t k, int32_t *data,
     }
     else
     {
+        if (int rc = ensure_wide(h)) return rc;
         if (nnz && data) TB_CUDA(cudaMemcpyAsync(data, h->d_data.ptr + h->nnzbase[k], nnz * sizeof(int), cudaMemcpyDefault, st));
         if (nnz && indices) TB_CUDA(cudaMemcpyAsync(indices, h->d_indices.ptr + h->nnzbase[k], nnz * sizeof(int), cudaMemcpyDefault, st));
     }
@@ -1386,6 +1440,7 @@ extern "C" int tb_hecke_copy_sparse(tb_hecke *h, int64_t k, int32_t *data, int32
     }
     else
     {
+        if (int rc = ensure_wide(h)) return rc;
         if (nnz && data) if (int rc = copy_out(h->g, data, h->d_data.ptr + h->nnzbase[k], nnz * sizeof(int))) return rc;
         if (nnz && indices) if (int rc = copy_out(h->g, indices, h->d_indices.ptr + h->nnzbase[k], nnz * sizeof(int))) return rc;
     }
@@ -1441,6 +1496,7 @@ extern "C" int tb_hecke_copy_dense(tb_hecke *h, int64_t k, int32_t *matrix)
     const int dim = (int)h->g->dims[k];
     const size_t cells = (size_t)rows * dim;
     if (cells == 0) return TB_OK;
+    if (int rc = ensure_wide(h)) return rc;
     cudaPointerAttributes attr;
     bool on_device = cudaPointerGetAttributes(&attr, matrix) == cudaSuccess &&
                      (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
