@@ -1455,10 +1455,13 @@ extern "C" int tb_hecke_copy_sparse(tb_hecke *h, int64_t k, int32_t *data, int32
 extern "C" int tb_host_widen_probe(int64_t entries, double *out_gbps, int *threads, int *avx2)
 {
     if (entries <= 0) return fail(TB_ERR_INVALID_ARGUMENT, "tb_host_widen_probe: bad size");
-    std::vector<unsigned short> idx((size_t)entries, 7);
-    std::vector<signed char> dat((size_t)entries, -3);
-    int32_t *oi = (int32_t *)aligned_alloc(64, (size_t)entries * 4), *od = (int32_t *)aligned_alloc(64, (size_t)entries * 4);
-    if (!oi || !od) return fail(TB_ERR_RUNTIME, "tb_host_widen_probe: out of memory");
+    std::vector<unsigned short> idx((size_t)entries);
+    std::vector<signed char> dat((size_t)entries);
+    for (int64_t i = 0; i < entries; ++i) { idx[i] = (unsigned short)(i * 7919); dat[i] = (signed char)(i * 37 - 3); }
+    // deliberately misaligned destinations: the streaming-store loops must handle any alignment
+    int32_t *oi_raw = (int32_t *)aligned_alloc(64, (size_t)entries * 4 + 64), *od_raw = (int32_t *)aligned_alloc(64, (size_t)entries * 4 + 64);
+    if (!oi_raw || !od_raw) return fail(TB_ERR_RUNTIME, "tb_host_widen_probe: out of memory");
+    int32_t *oi = oi_raw + 1, *od = od_raw + 3;
     memset(oi, 0, (size_t)entries * 4);
     memset(od, 0, (size_t)entries * 4);
     double best = 0;
@@ -1470,9 +1473,10 @@ extern "C" int tb_host_widen_probe(int64_t entries, double *out_gbps, int *threa
         const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         best = std::max(best, (double)entries * 8.0 / sec / 1e9);
     }
-    const bool ok = oi[entries - 1] == 7 && od[entries - 1] == -3 && oi[0] == 7 && od[0] == -3;
-    free(oi);
-    free(od);
+    bool ok = true;
+    for (int64_t i = 0; i < entries && ok; ++i) ok = oi[i] == (int32_t)idx[i] && od[i] == (int32_t)dat[i];
+    free(oi_raw);
+    free(od_raw);
     if (!ok) return fail(TB_ERR_RUNTIME, "tb_host_widen_probe: wrong result");
     if (out_gbps) *out_gbps = best;
     if (threads) *threads = HostPool::get().size();

@@ -65,3 +65,16 @@ def test_table_roundtrip(tables, tmp_path):
         assert np.array_equal(u.to_stream(), t.to_stream())
     assert tables("1062347").q[0].tolist() == [1, 187, 1467, -187, 0, 0]
     assert tables("1009091").N == 10316
+
+
+def test_host_widening_pool_without_gpu():
+    """The host half of the narrow read-back (uint16 / int8 -> int32 with the library's thread pool)
+    needs no GPU: the probe widens a buffer, checks the values and reports its throughput."""
+    import ctypes
+    from ternary_birch_b200 import cabi
+    L = cabi.lib()
+    gbps, threads, avx2 = ctypes.c_double(), ctypes.c_int(), ctypes.c_int()
+    for entries in (1, 7, 1 << 18, (1 << 20) + 13):
+        assert L.tb_host_widen_probe(entries, ctypes.byref(gbps), ctypes.byref(threads), ctypes.byref(avx2)) == 0
+        assert gbps.value > 0 and threads.value >= 2 and avx2.value in (0, 1)
+    assert L.tb_host_widen_probe(0, None, None, None) != 0
