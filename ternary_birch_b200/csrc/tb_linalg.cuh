@@ -337,6 +337,117 @@ __global__ void __launch_bounds__(256) la_update_kernel(LaCtx c, int c0, const i
     }
 }
 
+// The same update on the tensor cores.  A 29-bit residue is four 8-bit limbs, so the 32-term
+// product sum is sum_k 2^(8k) S_k with S_k = sum over limb pairs a + b = k of an 8-bit GEMM:
+// 16 `mma.m16n8k32.u8.u8.s32` per 16 x 8 output tile (K = 32 is exactly the panel width), seven
+// int32 accumulators (each at most 4 * 32 * 255^2 < 2^23), recombined in the epilogue into the
+// 64-bit sum the scalar kernel forms, then the same Montgomery fold.  64 x 128 tile per CTA,
+// eight warps of 16 rows x 64 columns.  Limb planes live in shared memory with a 48-byte row
+// stride (conflict-free fragment loads).
+#define TB_LA_LIMB_STRIDE 48
+
+__device__ __forceinline__ void la_mma_u8(int (&d)[4], const u32 (&a)[4], const u32 (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// four values -> their limb-th bytes packed into one word
+__device__ __forceinline__ u32 la_pack_limb(u32 v0, u32 v1, u32 v2, u32 v3, int limb)
+{
+    const u32 sel = 0x0040u + 0x0011u * (u32)limb;             // byte `limb` of the first and of the second operand
+    const u32 x = __byte_perm(v0, v1, sel), y = __byte_perm(v2, v3, sel);
+    return __byte_perm(x, y, 0x5410);
+}
+
+__global__ void __launch_bounds__(256) la_update_mma_kernel(LaCtx c, int c0, const int *tile_free)
+{
+    if ((blockIdx.x + 1) * TB_LA_TILE_COLS <= c0 && tile_free[blockIdx.x] == 0) return;
+    __shared__ __align__(16) unsigned char s_A[4][TB_LA_TILE_ROWS][TB_LA_LIMB_STRIDE];
+    __shared__ __align__(16) unsigned char s_B[4][TB_LA_TILE_COLS][TB_LA_LIMB_STRIDE];
+    const int col0 = blockIdx.x * TB_LA_TILE_COLS, row0 = blockIdx.y * TB_LA_TILE_ROWS;
+    // L tile: 64 rows x 32 values, four consecutive k per thread-item
+    for (int i = threadIdx.x; i < TB_LA_TILE_ROWS * (TB_LA_PANEL / 4); i += 256)
+    {
+        const int r = i / (TB_LA_PANEL / 4), q = i % (TB_LA_PANEL / 4);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row0 + r < c.rows) v = *reinterpret_cast<const uint4 *>(c.L + (size_t)(row0 + r) * TB_LA_PANEL + q * 4);
+#pragma unroll
+        for (int limb = 0; limb < 4; ++limb)
+            *reinterpret_cast<u32 *>(&s_A[limb][r][q * 4]) = la_pack_limb(v.x, v.y, v.z, v.w, limb);
+    }
+    // R tile: 32 k x 128 columns, transposed so that k runs along the bytes of a column's row
+    for (int i = threadIdx.x; i < TB_LA_TILE_COLS * (TB_LA_PANEL / 4); i += 256)
+    {
+        const int col = i % TB_LA_TILE_COLS, q = i / TB_LA_TILE_COLS;
+        const u32 *src = c.R + (size_t)(q * 4) * c.ld + col0 + col;
+        const u32 v0 = src[0], v1 = src[c.ld], v2 = src[2 * (size_t)c.ld], v3 = src[3 * (size_t)c.ld];
+#pragma unroll
+        for (int limb = 0; limb < 4; ++limb)
+            *reinterpret_cast<u32 *>(&s_B[limb][col][q * 4]) = la_pack_limb(v0, v1, v2, v3, limb);
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, tq = lane & 3;
+    const int wrow = (warp & 3) * 16, wcol = (warp >> 2) * 64;
+    u32 A[4][4];
+#pragma unroll
+    for (int limb = 0; limb < 4; ++limb)
+    {
+        A[limb][0] = *reinterpret_cast<const u32 *>(&s_A[limb][wrow + g][tq * 4]);
+        A[limb][1] = *reinterpret_cast<const u32 *>(&s_A[limb][wrow + g + 8][tq * 4]);
+        A[limb][2] = *reinterpret_cast<const u32 *>(&s_A[limb][wrow + g][16 + tq * 4]);
+        A[limb][3] = *reinterpret_cast<const u32 *>(&s_A[limb][wrow + g + 8][16 + tq * 4]);
+    }
+#pragma unroll 1
+    for (int nt = 0; nt < 8; ++nt)
+    {
+        const int ncol = wcol + nt * 8;
+        u32 B[4][2];
+#pragma unroll
+        for (int limb = 0; limb < 4; ++limb)
+        {
+            B[limb][0] = *reinterpret_cast<const u32 *>(&s_B[limb][ncol + g][tq * 4]);
+            B[limb][1] = *reinterpret_cast<const u32 *>(&s_B[limb][ncol + g][16 + tq * 4]);
+        }
+        int S[7][4];
+#pragma unroll
+        for (int k = 0; k < 7; ++k)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) S[k][e] = 0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) la_mma_u8(S[a + b], A[a], B[b]);
+        // fragment element e: row = g + 8 * (e >> 1), column = 2 * tq + (e & 1)
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+        {
+            const int row = row0 + wrow + g + 8 * half;
+            const int col = col0 + ncol + 2 * tq;
+            if (row >= c.rows || col >= c.ld) continue;
+            uint2 *ptr = reinterpret_cast<uint2 *>(c.M + (size_t)row * c.ld + col);
+            uint2 m = *ptr;
+            u32 mv[2] = {m.x, m.y};
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+            {
+                const int cc = col + b;
+                if (cc >= c0 && cc < c0 + TB_LA_PANEL) continue;      // panel columns are final already
+                const int e = half * 2 + b;
+                const u32 lo = (u32)S[0][e] + ((u32)S[1][e] << 8);                 // weights 2^0, 2^8    (< 2^31)
+                const u32 mid = (u32)S[2][e] + ((u32)S[3][e] << 8);                // weights 2^16, 2^24  (< 2^31)
+                const u32 hi = (u32)S[4][e] + ((u32)S[5][e] << 8) + ((u32)S[6][e] << 16);   // weights 2^32, 2^40, 2^48
+                const u64 acc = (u64)lo + ((u64)mid << 16) + ((u64)hi << 32);
+                mv[b] = la_sub(mv[b], la_fold(acc, c), c);
+            }
+            *ptr = make_uint2(mv[0], mv[1]);
+        }
+    }
+}
+
 // basis[m][free_col[m]] = 1, basis[m][piv_col[k]] = -M[piv_row[k]][free_col[m]]
 __global__ void la_kernel_basis_kernel(LaCtx c, const int *free_col, int dim, int rank, u32 *basis)
 {

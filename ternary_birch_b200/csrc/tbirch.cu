@@ -2103,6 +2103,7 @@ static int la_solve(int64_t rows, int64_t cols, uint32_t P, Fill fill, tb_modker
         int grid = (int)std::min<int64_t>((int64_t)sms * std::min(std::max(per_sm, 1), 1), (rows + warps_per_block - 1) / warps_per_block);
         grid = std::max(1, grid);
         const dim3 ugrid(tiles, (unsigned)((rows + TB_LA_TILE_ROWS - 1) / TB_LA_TILE_ROWS));
+        const bool use_mma = getenv("TBIRCH_LA_NO_MMA") == nullptr;     // 8-bit limb tensor-core update (default)
         for (int c0 = 0; c0 < c.cols; c0 += TB_LA_PANEL)
         {
             int *cand_ptr = cand.ptr, *tf_ptr = tile_free.ptr;
@@ -2110,7 +2111,8 @@ static int la_solve(int64_t rows, int64_t cols, uint32_t P, Fill fill, tb_modker
             TB_CUDA(cudaLaunchCooperativeKernel((void *)la_panel_kernel, dim3(grid), dim3(TB_LA_PANEL_THREADS), args, 0, 0));
             la_pivot_fix_kernel<<<1, TB_LA_PANEL * 32>>>(c, c0);
             la_pivot_rows_kernel<<<(c.cols + 127) / 128, 128>>>(c, c0);
-            la_update_kernel<<<ugrid, 256>>>(c, c0, tile_free.ptr);
+            if (use_mma) la_update_mma_kernel<<<ugrid, 256>>>(c, c0, tile_free.ptr);
+            else la_update_kernel<<<ugrid, 256>>>(c, c0, tile_free.ptr);
             g_launches += 4;
         }
         TB_CUDA(cudaGetLastError());
