@@ -265,6 +265,7 @@ struct tb_genus {
     struct Copier *copier = nullptr;   // background thread of the narrow read-back (started on first use)
     bool allow_narrow = true;     // TBIRCH_NO_NARROW_COPY turns the compressed read-back off
     int64_t narrow_min_nnz = 1 << 18;   // smaller matrices are copied as they are (TBIRCH_NARROW_MIN_NNZ)
+    int64_t narrow_max_ratio = 32;      // narrow row output is attempted while (p+1)/N stays below this (TBIRCH_NARROW_MAX_RATIO)
     bool allow_fused = true;
     bool force_checked = false;   // TBIRCH_FORCE_CHECKED: always run the checked C128 kernel in precise mode
     int last_int_mode = -1;       // tb_last_int_mode
@@ -483,6 +484,7 @@ extern "C" int tb_genus_create(const tb_genus_desc *d, tb_genus **out)
     // plain DMA: keep the narrow read-back for one or two processes per host
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) if (atoi(e) > 2 && !getenv("TBIRCH_FORCE_NARROW_COPY")) g->allow_narrow = false;
     if (const char *e = getenv("TBIRCH_NARROW_MIN_NNZ")) g->narrow_min_nnz = std::max(1ll, atoll(e));
+    if (const char *e = getenv("TBIRCH_NARROW_MAX_RATIO")) g->narrow_max_ratio = std::max(1ll, atoll(e));
     TB_CUDA(g->d_err.reserve(2));
     TB_CUDA(g->d_tab.reserve(3 * (size_t)C));
     TB_CUDA(g->d_nnz.reserve(2 * (size_t)C));
@@ -866,7 +868,7 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     int64_t max_dim = 0;
     for (int k = 0; k < C; ++k) max_dim = std::max<int64_t>(max_dim, g->dims[k]);
     const bool narrow_possible = g->allow_narrow && max_dim <= 65536 && cap_total >= g->narrow_min_nnz &&
-                                 (P1 <= 127 || (int64_t)P1 <= 32 * (int64_t)N);
+                                 (P1 <= 127 || (int64_t)P1 <= g->narrow_max_ratio * (int64_t)N);
 
     RowLaunch R;
     memset(&R, 0, sizeof(R));

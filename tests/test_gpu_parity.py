@@ -369,3 +369,36 @@ def test_narrow_readback_matches_plain(tables, monkeypatch, name, p, want_narrow
     for k in got[False]:
         for a, b in zip(got[False][k], got[True][k]):
             assert np.array_equal(a, b), k
+
+
+@pytest.mark.parametrize("env", [dict(TBIRCH_TWO_PASS_ROWS="1"), dict(TBIRCH_TWO_PASS_ROWS="1", TBIRCH_NARROW_MIN_NNZ="1"),
+                                 dict(TBIRCH_NARROW_MIN_NNZ="1", TBIRCH_NARROW_MAX_RATIO="100000"),
+                                 dict(TBIRCH_TWO_PASS_ROWS="1", TBIRCH_NARROW_MIN_NNZ="1", TBIRCH_NARROW_MAX_RATIO="100000")])
+def test_row_kernel_variants_agree(tables, port_oracle, monkeypatch, env):
+    """The row phase has a fused single-pass form and a count/scan/fill form, each with int32 or narrow
+    output.  With the narrow attempt forced at p = 16381 >> N = 130 an entry exceeds 8 bits, so the fused form
+    must redo the row pass in int32 and the two-pass form must pick int32 after its count pass.  All variants
+    equal the oracle."""
+    from ternary_birch_b200 import Genus
+    for k in ("TBIRCH_TWO_PASS_ROWS", "TBIRCH_NARROW_MIN_NNZ", "TBIRCH_NARROW_MAX_RATIO", "TBIRCH_NO_NARROW_COPY"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    t = tables("85085")
+    g = Genus(t, precise=True)
+    try:
+        for p in (19, 997, 16381):
+            res = g.hecke_device(p)
+            got = {int(res.conductor(k)): res.sparse(k) for k in range(res.num_conductors())}
+            dense0 = g.hecke_matrix_dense(p)[1]
+            res.close()
+            assert_same_csr(got, port_oracle("85085").hecke(p, True), (env, p))
+            data, indices, indptr = got[1]
+            want = np.zeros((t.N, t.N), dtype=np.int32)
+            for r in range(t.N):
+                want[r, indices[indptr[r]:indptr[r + 1]]] = data[indptr[r]:indptr[r + 1]]
+            assert np.array_equal(dense0, want), (env, p)
+            if p == 16381:
+                assert np.abs(data).max() > 127          # the case the int32 fallback exists for
+    finally:
+        g.close()
