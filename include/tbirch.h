@@ -115,6 +115,11 @@ int64_t tb_hecke_nnz(const tb_hecke *h, int64_t k);
 /* CSR triple in the reference's order (data, indices, indptr), Genus.h:662-671:
  * data[nnz], indices[nnz], indptr[rows+1]. */
 int tb_hecke_copy_sparse(tb_hecke *h, int64_t k, int32_t *data, int32_t *indices, int32_t *indptr);
+/* All conductors in one call, into three concatenated arrays: data_all / indices_all hold the
+ * tb_hecke_nnz(h, k) entries of conductor 0, 1, ... back to back, indptr_all the
+ * (tb_hecke_rows(h, k) + 1)-blocks.  Same values as 2^K tb_hecke_copy_sparse calls, a fraction
+ * of their fixed costs. */
+int tb_hecke_copy_sparse_all(tb_hecke *h, int32_t *data_all, int32_t *indices_all, int32_t *indptr_all);
 /* Same copy without synchronising: lets the caller overlap the read-back of one T_p with the
  * next one.  Device destinations and small matrices are enqueued on `cuda_stream`; large host
  * destinations are served by the library's background read-back.  Either way

@@ -58,3 +58,12 @@ for precise in (False, True):
     b.compute_eigenvalues_upto(1000, precise=precise, force=True)
     out[f"C3_eigenvalues_upto_1000_{'precise' if precise else 'int64'}_ms"] = 1e3 * (time.perf_counter() - t0)
 print(json.dumps(out, indent=1))
+
+# C4-size call into fresh numpy arrays (pageable memory): the whole hecke_matrix_sparse(9973)
+t = load_genus_table(G / "genus_1009091.npz")
+g = Genus(t, precise=False)
+g.hecke_matrix_sparse(107)
+t0 = time.perf_counter()
+m = g.hecke_matrix_sparse(9973)
+print(json.dumps({"C4_T9973_sparse_into_numpy_ms": 1e3 * (time.perf_counter() - t0),
+                  "C4_T9973_bytes": int(sum(a.nbytes for trio in m.values() for a in trio))}))

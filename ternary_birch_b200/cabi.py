@@ -46,6 +46,7 @@ def lib() -> ctypes.CDLL:
     L.tb_last_kernel_time.argtypes = [vp, vp, vp, vp]
     L.tb_last_int_mode.argtypes = [vp]
     L.tb_hecke_copy_wait.argtypes = [vp]
+    L.tb_hecke_copy_sparse_all.argtypes = [vp, vp, vp, vp]
     L.tb_hecke_transfer_bytes.argtypes = [vp, i64]
     L.tb_hecke_transfer_bytes.restype = i64
     L.tb_host_widen_probe.argtypes = [i64, vp, vp, vp]
@@ -110,7 +111,7 @@ EXPORTS = [
     "tb_genus_num_conductors", "tb_genus_conductor", "tb_genus_dim",
     "tb_hecke_compute", "tb_hecke_compute_rows", "tb_hecke_num_conductors", "tb_hecke_conductor",
     "tb_hecke_dim", "tb_hecke_rows", "tb_hecke_row_begin", "tb_hecke_nnz", "tb_hecke_copy_sparse",
-    "tb_hecke_copy_sparse_async", "tb_hecke_copy_wait", "tb_hecke_transfer_bytes", "tb_host_widen_probe",
+    "tb_hecke_copy_sparse_async", "tb_hecke_copy_sparse_all", "tb_hecke_copy_wait", "tb_hecke_transfer_bytes", "tb_host_widen_probe",
     "tb_hecke_copy_dense", "tb_hecke_destroy", "tb_eigenvalues", "tb_isoseq_open", "tb_isoseq_done",
     "tb_isoseq_next", "tb_isoseq_read", "tb_isoseq_close", "tb_neighbor_records", "tb_int_peak",
     "tb_quad_form", "tb_genus_enumerate", "tb_table_desc", "tb_table_destroy",

@@ -656,6 +656,29 @@ __global__ void widen_device_kernel(const unsigned short *idx16, const signed ch
     }
 }
 
+// All conductors' data / indices, packed back to back (conductor-major) for a single read-back.
+// grid.y = conductor; src offsets are the per-conductor regions, dst offsets the running totals.
+__global__ void pack_all_kernel(const int *data, const int *indices, const unsigned short *idx16, const signed char *dat8,
+                                const i64 *nnzbase, const i64 *nnz, const i64 *dstbase, int *data_out, int *indices_out)
+{
+    const int k = blockIdx.y;
+    const i64 n = nnz[k], src = nnzbase[k], dst = dstbase[k];
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        if (data)
+        {
+            data_out[dst + i] = data[src + i];
+            indices_out[dst + i] = indices[src + i];
+        }
+        else
+        {
+            data_out[dst + i] = (int)dat8[src + i];
+            indices_out[dst + i] = (int)idx16[src + i];
+        }
+    }
+}
+
 // Dense rows from the CSR rows of one conductor.
 __global__ void dense_scatter_kernel(const int *indptr, const int *data, const int *indices, int rows, int dim, int *matrix)
 {

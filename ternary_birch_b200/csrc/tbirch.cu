@@ -1016,91 +1016,6 @@ extern "C" int64_t tb_hecke_rows(const tb_hecke *h, int64_t k) { return h->rows[
 extern "C" int64_t tb_hecke_row_begin(const tb_hecke *h, int64_t k) { return h->rowfirst[k]; }
 extern "C" int64_t tb_hecke_nnz(const tb_hecke *h, int64_t k) { return h->nnz[k]; }
 
-// Device -> caller copy.  Device or pinned destinations take one cudaMemcpyAsync; pageable
-// host memory (a std::vector, a numpy array) would make the driver stage through its own small
-// buffer at a few GB/s, so it is pipelined through two pinned 32 MB buffers instead: the DMA
-// of chunk i overlaps the host memcpy of chunk i-1.
-static const size_t TB_STAGE_BYTES = (size_t)32 << 20;
-
-static int copy_out(tb_genus *g, void *dst, const void *src_dev, size_t bytes)
-{
-    if (bytes == 0) return TB_OK;
-    cudaStream_t st = g->stream;
-    cudaPointerAttributes attr;
-    const bool known = cudaPointerGetAttributes(&attr, dst) == cudaSuccess;
-    cudaGetLastError();
-    if (known && attr.type != cudaMemoryTypeUnregistered)
-    {
-        TB_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDefault, st));
-        return TB_OK;                                  // caller synchronises
-    }
-    for (int i = 0; i < 2; ++i)
-        if (!g->h_stage[i])
-        {
-            TB_CUDA(cudaMallocHost((void **)&g->h_stage[i], TB_STAGE_BYTES));
-            TB_CUDA(cudaEventCreateWithFlags(&g->ev_stage[i], cudaEventDisableTiming));
-        }
-    const size_t chunks = (bytes + TB_STAGE_BYTES - 1) / TB_STAGE_BYTES;
-    for (size_t c = 0; c <= chunks; ++c)
-    {
-        if (c < chunks)
-        {
-            const size_t off = c * TB_STAGE_BYTES, len = std::min(TB_STAGE_BYTES, bytes - off);
-            TB_CUDA(cudaMemcpyAsync(g->h_stage[c & 1], (const char *)src_dev + off, len, cudaMemcpyDeviceToHost, st));
-            TB_CUDA(cudaEventRecord(g->ev_stage[c & 1], st));
-        }
-        if (c > 0)
-        {
-            const size_t off = (c - 1) * TB_STAGE_BYTES, len = std::min(TB_STAGE_BYTES, bytes - off);
-            TB_CUDA(cudaEventSynchronize(g->ev_stage[(c - 1) & 1]));
-            memcpy((char *)dst + off, g->h_stage[(c - 1) & 1], len);
-        }
-    }
-    return TB_OK;
-}
-
-// ---------------------------------------------------------------------------
-// Narrow read-back.  A T_p at the bench size is 3.6 GB of int32 CSR; PCIe moves it at
-// ~54 GB/s, three times longer than the GPU needs to compute it.  When every column index
-// fits 16 bits and every |entry| fits 8 (known from the row kernel's max-multiplicity word),
-// the device packs indices/entries to 3 bytes per entry, the DMA moves those into pinned
-// staging, and host threads widen them into the caller's int32 arrays with streaming stores.
-// Two internal streams alternate chunks so the DMA of one chunk overlaps the widening of
-// the previous one; the caller's stream waits on both.
-// ---------------------------------------------------------------------------
-static const size_t TB_NARROW_CHUNK = (size_t)16 << 20;      // entries per chunk (48 MB of staging)
-
-__attribute__((target("avx2"))) static void widen_u16_avx2(const unsigned short *src, int32_t *dst, size_t n)
-{
-    size_t i = 0;
-    while (i < n && ((uintptr_t)(dst + i) & 31)) { dst[i] = src[i]; ++i; }
-    for (; i + 8 <= n; i += 8)
-        _mm256_stream_si256((__m256i *)(dst + i), _mm256_cvtepu16_epi32(_mm_loadu_si128((const __m128i *)(src + i))));
-    for (; i < n; ++i) dst[i] = src[i];
-    _mm_sfence();
-}
-__attribute__((target("avx2"))) static void widen_i8_avx2(const signed char *src, int32_t *dst, size_t n)
-{
-    size_t i = 0;
-    while (i < n && ((uintptr_t)(dst + i) & 31)) { dst[i] = src[i]; ++i; }
-    for (; i + 8 <= n; i += 8)
-        _mm256_stream_si256((__m256i *)(dst + i), _mm256_cvtepi8_epi32(_mm_loadl_epi64((const __m128i *)(src + i))));
-    for (; i < n; ++i) dst[i] = src[i];
-    _mm_sfence();
-}
-static void widen_u16(const unsigned short *src, int32_t *dst, size_t n)
-{
-    static const bool avx2 = __builtin_cpu_supports("avx2");
-    if (avx2) { widen_u16_avx2(src, dst, n); return; }
-    for (size_t i = 0; i < n; ++i) dst[i] = src[i];
-}
-static void widen_i8(const signed char *src, int32_t *dst, size_t n)
-{
-    static const bool avx2 = __builtin_cpu_supports("avx2");
-    if (avx2) { widen_i8_avx2(src, dst, n); return; }
-    for (size_t i = 0; i < n; ++i) dst[i] = src[i];
-}
-
 // A small process-wide pool: parallel_for over [0, n) in `parts` slices.
 class HostPool {
 public:
@@ -1180,6 +1095,104 @@ private:
     uint64_t epoch = 0;
     bool stop = false;
 };
+
+// memcpy into pageable memory with the pool: fresh numpy arrays / std::vectors take a page fault per
+// 4 KB on first touch, which parallelises across threads
+static void parallel_memcpy(void *dst, const void *src, size_t bytes)
+{
+    const size_t slice = (size_t)1 << 20;
+    if (bytes < 4 * slice) { memcpy(dst, src, bytes); return; }
+    const int parts = (int)((bytes + slice - 1) / slice);
+    HostPool::get().run(parts, [=](int i) {
+        const size_t lo = (size_t)i * slice;
+        memcpy((char *)dst + lo, (const char *)src + lo, std::min(slice, bytes - lo));
+    });
+}
+
+// Device -> caller copy.  Device or pinned destinations take one cudaMemcpyAsync; pageable
+// host memory (a std::vector, a numpy array) would make the driver stage through its own small
+// buffer at a few GB/s, so it is pipelined through two pinned 32 MB buffers instead: the DMA
+// of chunk i overlaps the host memcpy of chunk i-1.
+static const size_t TB_STAGE_BYTES = (size_t)32 << 20;
+
+static int copy_out(tb_genus *g, void *dst, const void *src_dev, size_t bytes)
+{
+    if (bytes == 0) return TB_OK;
+    cudaStream_t st = g->stream;
+    cudaPointerAttributes attr;
+    const bool known = cudaPointerGetAttributes(&attr, dst) == cudaSuccess;
+    cudaGetLastError();
+    if (known && attr.type != cudaMemoryTypeUnregistered)
+    {
+        TB_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDefault, st));
+        return TB_OK;                                  // caller synchronises
+    }
+    for (int i = 0; i < 2; ++i)
+        if (!g->h_stage[i])
+        {
+            TB_CUDA(cudaMallocHost((void **)&g->h_stage[i], TB_STAGE_BYTES));
+            TB_CUDA(cudaEventCreateWithFlags(&g->ev_stage[i], cudaEventDisableTiming));
+        }
+    const size_t chunks = (bytes + TB_STAGE_BYTES - 1) / TB_STAGE_BYTES;
+    for (size_t c = 0; c <= chunks; ++c)
+    {
+        if (c < chunks)
+        {
+            const size_t off = c * TB_STAGE_BYTES, len = std::min(TB_STAGE_BYTES, bytes - off);
+            TB_CUDA(cudaMemcpyAsync(g->h_stage[c & 1], (const char *)src_dev + off, len, cudaMemcpyDeviceToHost, st));
+            TB_CUDA(cudaEventRecord(g->ev_stage[c & 1], st));
+        }
+        if (c > 0)
+        {
+            const size_t off = (c - 1) * TB_STAGE_BYTES, len = std::min(TB_STAGE_BYTES, bytes - off);
+            TB_CUDA(cudaEventSynchronize(g->ev_stage[(c - 1) & 1]));
+            parallel_memcpy((char *)dst + off, g->h_stage[(c - 1) & 1], len);
+        }
+    }
+    return TB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Narrow read-back.  A T_p at the bench size is 3.6 GB of int32 CSR; PCIe moves it at
+// ~54 GB/s, three times longer than the GPU needs to compute it.  When every column index
+// fits 16 bits and every |entry| fits 8 (known from the row kernel's max-multiplicity word),
+// the device packs indices/entries to 3 bytes per entry, the DMA moves those into pinned
+// staging, and host threads widen them into the caller's int32 arrays with streaming stores.
+// Two internal streams alternate chunks so the DMA of one chunk overlaps the widening of
+// the previous one; the caller's stream waits on both.
+// ---------------------------------------------------------------------------
+static const size_t TB_NARROW_CHUNK = (size_t)16 << 20;      // entries per chunk (48 MB of staging)
+
+__attribute__((target("avx2"))) static void widen_u16_avx2(const unsigned short *src, int32_t *dst, size_t n)
+{
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 31)) { dst[i] = src[i]; ++i; }
+    for (; i + 8 <= n; i += 8)
+        _mm256_stream_si256((__m256i *)(dst + i), _mm256_cvtepu16_epi32(_mm_loadu_si128((const __m128i *)(src + i))));
+    for (; i < n; ++i) dst[i] = src[i];
+    _mm_sfence();
+}
+__attribute__((target("avx2"))) static void widen_i8_avx2(const signed char *src, int32_t *dst, size_t n)
+{
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 31)) { dst[i] = src[i]; ++i; }
+    for (; i + 8 <= n; i += 8)
+        _mm256_stream_si256((__m256i *)(dst + i), _mm256_cvtepi8_epi32(_mm_loadl_epi64((const __m128i *)(src + i))));
+    for (; i < n; ++i) dst[i] = src[i];
+    _mm_sfence();
+}
+static void widen_u16(const unsigned short *src, int32_t *dst, size_t n)
+{
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) { widen_u16_avx2(src, dst, n); return; }
+    for (size_t i = 0; i < n; ++i) dst[i] = src[i];
+}
+static void widen_i8(const signed char *src, int32_t *dst, size_t n)
+{
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) { widen_i8_avx2(src, dst, n); return; }
+    for (size_t i = 0; i < n; ++i) dst[i] = src[i];
+}
 
 struct WidenJob {
     const unsigned short *idx16;
@@ -1447,6 +1460,65 @@ extern "C" int tb_hecke_copy_sparse(tb_hecke *h, int64_t k, int32_t *data, int32
         if (nnz && indices) if (int rc = copy_out(h->g, indices, h->d_indices.ptr + h->nnzbase[k], nnz * sizeof(int))) return rc;
     }
     if (indptr) if (int rc = copy_out(h->g, indptr, h->d_indptr.ptr + h->rowbase[k], ((size_t)h->rows[k] + 1) * sizeof(int))) return rc;
+    TB_CUDA(cudaStreamSynchronize(st));
+    return tb_hecke_copy_wait(h);
+}
+
+// Every conductor at once into three concatenated host (or device) arrays: data_all / indices_all hold the
+// nnz[k] entries of conductor 0, 1, ... back to back, indptr_all the (rows[k] + 1)-blocks.  One packing
+// kernel and three copies instead of 3 * 2^K small ones; large results use the per-conductor narrow
+// read-back into the slices instead.
+extern "C" int tb_hecke_copy_sparse_all(tb_hecke *h, int32_t *data_all, int32_t *indices_all, int32_t *indptr_all)
+{
+    if (!h) return fail(TB_ERR_INVALID_ARGUMENT, "tb_hecke_copy_sparse_all: null argument");
+    tb_genus *g = h->g;
+    cudaStream_t st = g->stream;
+    const int C = h->C;
+    std::vector<i64> meta(3 * (size_t)C);
+    i64 total = 0;
+    int total_ptr = 0;
+    bool any_narrow = false;
+    for (int k = 0; k < C; ++k)
+    {
+        meta[k] = h->nnzbase[k]; meta[C + k] = h->nnz[k]; meta[2 * C + k] = total;
+        if (h->nnz[k] && data_all && indices_all && narrow_applies(h, k, data_all + total, indices_all + total)) any_narrow = true;
+        total += h->nnz[k];
+        total_ptr += h->rows[k] + 1;
+    }
+    if (indptr_all) if (int rc = copy_out(g, indptr_all, h->d_indptr.ptr, (size_t)total_ptr * sizeof(int))) return rc;
+    if (total && data_all && indices_all)
+    {
+        if (any_narrow)
+        {
+            i64 off = 0;
+            for (int k = 0; k < C; ++k)
+            {
+                if (int rc = tb_hecke_copy_sparse_async(h, k, data_all + off, indices_all + off, nullptr, st)) return rc;
+                off += h->nnz[k];
+            }
+        }
+        else
+        {
+            PoolBuf<i64> d_meta;
+            PoolBuf<int> d_pack;
+            TB_CUDA(d_meta.reserve(meta.size(), st));
+            TB_CUDA(d_pack.reserve(2 * (size_t)total, st));
+            TB_CUDA(cudaMemcpyAsync(d_meta.ptr, meta.data(), meta.size() * sizeof(i64), cudaMemcpyHostToDevice, st));
+            const bool wide = h->wide_valid;
+            const unsigned bx = (unsigned)std::min<i64>((total / C + 255) / 256 + 1, 148 * 8);
+            pack_all_kernel<<<dim3(bx, C), 256, 0, st>>>(wide ? h->d_data.ptr : nullptr, wide ? h->d_indices.ptr : nullptr,
+                                                         h->d_idx16.ptr, h->d_dat8.ptr, d_meta.ptr, d_meta.ptr + C,
+                                                         d_meta.ptr + 2 * C, d_pack.ptr, d_pack.ptr + total);
+            ++g_launches;
+            TB_CUDA(cudaGetLastError());
+            int rc = copy_out(g, data_all, d_pack.ptr, (size_t)total * sizeof(int));
+            if (!rc) rc = copy_out(g, indices_all, d_pack.ptr + total, (size_t)total * sizeof(int));
+            cudaStreamSynchronize(st);
+            d_meta.release();
+            d_pack.release();
+            if (rc) return rc;
+        }
+    }
     TB_CUDA(cudaStreamSynchronize(st));
     return tb_hecke_copy_wait(h);
 }

@@ -185,14 +185,20 @@ class Genus:
         L = cabi.lib()
         h = self._hecke(p, rep_begin, rep_end)
         try:
-            out = {}
-            for k in range(L.tb_hecke_num_conductors(h)):
-                nnz, rows = L.tb_hecke_nnz(h, k), L.tb_hecke_rows(h, k)
-                data = np.empty(nnz, dtype=np.int32)
-                indices = np.empty(nnz, dtype=np.int32)
-                indptr = np.empty(rows + 1, dtype=np.int32)
-                cabi.check(L.tb_hecke_copy_sparse(h, k, _ptr(data), _ptr(indices), _ptr(indptr)))
-                out[int(L.tb_hecke_conductor(h, k))] = [data, indices, indptr]
+            # one read-back of all conductors into three arrays; the per-conductor results are views
+            C = L.tb_hecke_num_conductors(h)
+            nnz = [L.tb_hecke_nnz(h, k) for k in range(C)]
+            rows = [L.tb_hecke_rows(h, k) for k in range(C)]
+            data = np.empty(sum(nnz), dtype=np.int32)
+            indices = np.empty(sum(nnz), dtype=np.int32)
+            indptr = np.empty(sum(rows) + C, dtype=np.int32)
+            cabi.check(L.tb_hecke_copy_sparse_all(h, _ptr(data), _ptr(indices), _ptr(indptr)))
+            out, a, b = {}, 0, 0
+            for k in range(C):
+                out[int(L.tb_hecke_conductor(h, k))] = [data[a:a + nnz[k]], indices[a:a + nnz[k]],
+                                                        indptr[b:b + rows[k] + 1]]
+                a += nnz[k]
+                b += rows[k] + 1
             return out
         finally:
             L.tb_hecke_destroy(h)
