@@ -1181,14 +1181,41 @@ __attribute__((target("avx2"))) static void widen_i8_avx2(const signed char *src
     for (; i < n; ++i) dst[i] = src[i];
     _mm_sfence();
 }
+// AVX-512: one streaming store per 64-byte line
+__attribute__((target("avx512f"))) static void widen_u16_avx512(const unsigned short *src, int32_t *dst, size_t n)
+{
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 63)) { dst[i] = src[i]; ++i; }
+    for (; i + 16 <= n; i += 16)
+        _mm512_stream_si512((__m512i *)(dst + i), _mm512_cvtepu16_epi32(_mm256_loadu_si256((const __m256i *)(src + i))));
+    for (; i < n; ++i) dst[i] = src[i];
+    _mm_sfence();
+}
+__attribute__((target("avx512f"))) static void widen_i8_avx512(const signed char *src, int32_t *dst, size_t n)
+{
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 63)) { dst[i] = src[i]; ++i; }
+    for (; i + 16 <= n; i += 16)
+        _mm512_stream_si512((__m512i *)(dst + i), _mm512_cvtepi8_epi32(_mm_loadu_si128((const __m128i *)(src + i))));
+    for (; i < n; ++i) dst[i] = src[i];
+    _mm_sfence();
+}
+static int widen_isa()
+{
+    static const int isa = getenv("TBIRCH_NO_AVX512") == nullptr && __builtin_cpu_supports("avx512f") ? 2
+                           : __builtin_cpu_supports("avx2") ? 1 : 0;
+    return isa;
+}
 static void widen_u16(const unsigned short *src, int32_t *dst, size_t n)
 {
+    if (widen_isa() == 2) { widen_u16_avx512(src, dst, n); return; }
     static const bool avx2 = __builtin_cpu_supports("avx2");
     if (avx2) { widen_u16_avx2(src, dst, n); return; }
     for (size_t i = 0; i < n; ++i) dst[i] = src[i];
 }
 static void widen_i8(const signed char *src, int32_t *dst, size_t n)
 {
+    if (widen_isa() == 2) { widen_i8_avx512(src, dst, n); return; }
     static const bool avx2 = __builtin_cpu_supports("avx2");
     if (avx2) { widen_i8_avx2(src, dst, n); return; }
     for (size_t i = 0; i < n; ++i) dst[i] = src[i];
@@ -1554,7 +1581,7 @@ extern "C" int tb_host_widen_probe(int64_t entries, double *out_gbps, int *threa
     if (!ok) return fail(TB_ERR_RUNTIME, "tb_host_widen_probe: wrong result");
     if (out_gbps) *out_gbps = best;
     if (threads) *threads = HostPool::get().size();
-    if (avx2) *avx2 = __builtin_cpu_supports("avx2") ? 1 : 0;
+    if (avx2) *avx2 = widen_isa();              // 0 scalar, 1 AVX2, 2 AVX-512
     return TB_OK;
 }
 

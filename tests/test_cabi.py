@@ -76,5 +76,5 @@ def test_host_widening_pool_without_gpu():
     gbps, threads, avx2 = ctypes.c_double(), ctypes.c_int(), ctypes.c_int()
     for entries in (1, 7, 1 << 18, (1 << 20) + 13):
         assert L.tb_host_widen_probe(entries, ctypes.byref(gbps), ctypes.byref(threads), ctypes.byref(avx2)) == 0
-        assert gbps.value > 0 and threads.value >= 2 and avx2.value in (0, 1)
+        assert gbps.value > 0 and threads.value >= 2 and avx2.value in (0, 1, 2)
     assert L.tb_host_widen_probe(0, None, None, None) != 0
