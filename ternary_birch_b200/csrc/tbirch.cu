@@ -1161,7 +1161,12 @@ static int copy_out(tb_genus *g, void *dst, const void *src_dev, size_t bytes)
 // Two internal streams alternate chunks so the DMA of one chunk overlaps the widening of
 // the previous one; the caller's stream waits on both.
 // ---------------------------------------------------------------------------
-static const size_t TB_NARROW_CHUNK = (size_t)16 << 20;      // entries per chunk (48 MB of staging)
+static size_t narrow_chunk_entries()
+{
+    static const size_t n = getenv("TBIRCH_NARROW_CHUNK") ? std::max<size_t>(1 << 16, (size_t)atoll(getenv("TBIRCH_NARROW_CHUNK"))) : ((size_t)16 << 20);
+    return n;   // entries per chunk (48 MB of staging by default)
+}
+#define TB_NARROW_CHUNK (narrow_chunk_entries())
 
 __attribute__((target("avx2"))) static void widen_u16_avx2(const unsigned short *src, int32_t *dst, size_t n)
 {

@@ -173,3 +173,27 @@ def test_batch_flow_against_elliptic_curves(tmp_path):
     assert res.rational_eigenvectors_count == 2 and res.dimension_total == sum(res.dimensions_by_conductor.values())
     assert res.job.eigenvalues_upto == batch.sturm_bound(37) == 7
     assert sorted(v["aps"][7] for v in res.rational_eigenvectors) == [-1, -1]
+
+
+# Number of isogeny classes of elliptic curves of each squarefree conductor 11 <= N <= 130 (Cremona's tables):
+# by modularity, the number of rational newforms of level N.
+CREMONA_CLASS_COUNTS = {
+    11: 1, 13: 0, 14: 1, 15: 1, 17: 1, 19: 1, 21: 1, 22: 0, 23: 0, 26: 2, 29: 0, 30: 1, 31: 0, 33: 1, 34: 1, 35: 1, 37: 2,
+    38: 2, 39: 1, 41: 0, 42: 1, 43: 1, 46: 1, 47: 0, 51: 1, 53: 1, 55: 1, 57: 3, 58: 2, 59: 0, 61: 1, 62: 1, 65: 1, 66: 3,
+    67: 1, 69: 1, 70: 1, 71: 0, 73: 1, 74: 0, 77: 3, 78: 1, 79: 1, 82: 1, 83: 1, 85: 1, 86: 0, 87: 0, 89: 2, 91: 2, 93: 0,
+    94: 1, 95: 0, 97: 0, 101: 1, 102: 3, 103: 0, 105: 1, 106: 4, 107: 0, 109: 1, 110: 3, 111: 0, 113: 1, 114: 3, 115: 1,
+    118: 4, 119: 0, 122: 1, 123: 2, 127: 0, 129: 2, 130: 3,
+}
+
+
+@pytest.mark.gpu
+def test_rational_newform_counts_match_cremona(tmp_path):
+    """Every squarefree level from 11 to 130 through the batch flow (genus on the GPU, eigenvector search,
+    oldform removal at levels with an even number of prime factors): the number of rational eigenvectors
+    equals the number of isogeny classes of elliptic curves of that conductor."""
+    got = {}
+    with EigenvectorDatabase(str(tmp_path / "e.sqlite3")) as db:
+        for level in CREMONA_CLASS_COUNTS:
+            assert batch.is_squarefree(level)
+            got[level] = len(db.get_genus_with_eigenvectors(level, precise=False).rational_eigenvectors())
+    assert got == CREMONA_CLASS_COUNTS
