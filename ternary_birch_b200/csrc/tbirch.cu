@@ -2126,15 +2126,32 @@ struct tb_modkernel {
 
 template <class T>
 struct LaBuf {
+    // stream-ordered pool allocations (default stream): a search runs hundreds of small eliminations, and
+    // cudaMalloc / cudaFree would cost more than they do
     T *ptr = nullptr;
-    ~LaBuf() { if (ptr) cudaFree(ptr); }
+    ~LaBuf() { if (ptr) cudaFreeAsync(ptr, 0); }
     cudaError_t alloc(size_t n, bool zero)
     {
-        cudaError_t e = cudaMalloc((void **)&ptr, std::max<size_t>(n, 1) * sizeof(T));
-        if (e == cudaSuccess && zero) e = cudaMemset(ptr, 0, std::max<size_t>(n, 1) * sizeof(T));
+        cudaError_t e = cudaMallocAsync((void **)&ptr, std::max<size_t>(n, 1) * sizeof(T), 0);
+        if (e != cudaSuccess) { ptr = nullptr; return e; }
+        if (zero) e = cudaMemsetAsync(ptr, 0, std::max<size_t>(n, 1) * sizeof(T), 0);
         return e;
     }
 };
+
+static void la_keep_pool()
+{
+    static bool done = false;
+    if (done) return;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+    {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done = true;
+}
 
 static bool la_is_prime(uint32_t n)
 {
@@ -2155,6 +2172,7 @@ static int la_solve(int64_t rows, int64_t cols, uint32_t P, Fill fill, tb_modker
     if (P < 3 || P >= (1u << 29) || !la_is_prime(P))
         return fail(TB_ERR_INVALID_ARGUMENT, "tb_modkernel: P must be an odd prime below 2^29");
     if (int rc = require_device()) return rc;
+    la_keep_pool();
     std::unique_ptr<tb_modkernel> k(new tb_modkernel);
     k->rows = rows; k->cols = cols; k->P = P;
     if (cols == 0) { *out = k.release(); return TB_OK; }
@@ -2182,7 +2200,7 @@ static int la_solve(int64_t rows, int64_t cols, uint32_t P, Fill fill, tb_modker
     TB_CUDA(lp.alloc(TB_LA_PANEL * TB_LA_PANEL, true));
     TB_CUDA(inv.alloc(TB_LA_PANEL, true));
     TB_CUDA(row_pivot.alloc(rows, false));
-    TB_CUDA(cudaMemset(row_pivot.ptr, 0xff, std::max<size_t>(rows, 1) * sizeof(int)));
+    TB_CUDA(cudaMemsetAsync(row_pivot.ptr, 0xff, std::max<size_t>(rows, 1) * sizeof(int), 0));
     TB_CUDA(piv_row.alloc(maxpiv, true));
     TB_CUDA(piv_col.alloc(maxpiv, true));
     TB_CUDA(rank.alloc(1, true));
