@@ -220,7 +220,7 @@ class Genus:
 
     def hecke_device(self, p: int, rep_begin=None, rep_end=None) -> "HeckeResult":
         """T_p left resident on the device (bench `value`; multi-GPU gather)."""
-        return HeckeResult(self._hecke(p, rep_begin, rep_end))
+        return HeckeResult(self._hecke(p, rep_begin, rep_end), owner=self)
 
     def eigenvector(self, vec, conductor: int) -> Eigenvector:
         """Genus<R>::eigenvector (Genus.h:350-390)."""
@@ -276,8 +276,9 @@ class Genus:
 class HeckeResult:
     """All 2^K matrices of one T_p, resident on the device until copied."""
 
-    def __init__(self, handle):
+    def __init__(self, handle, owner=None):
         self._h = handle
+        self._owner = owner          # the result reads its genus (streams, copier): keep it alive
 
     def num_conductors(self) -> int:
         return int(cabi.lib().tb_hecke_num_conductors(self._h))
