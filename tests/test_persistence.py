@@ -197,3 +197,27 @@ def test_rational_newform_counts_match_cremona(tmp_path):
             assert batch.is_squarefree(level)
             got[level] = len(db.get_genus_with_eigenvectors(level, precise=False).rational_eigenvectors())
     assert got == CREMONA_CLASS_COUNTS
+
+
+@pytest.mark.gpu
+def test_generate_eigenvalues_script(tmp_path):
+    """The batch driver's command line (reference: scripts/generate_eigenvalues.py:169-231): one JSON per
+    squarefree level of the range, loadable, with eigenvalues up to the Sturm bound of the ramified part."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    out = tmp_path / "json"
+    r = subprocess.run([sys.executable, str(root / "scripts" / "generate_eigenvalues.py"), str(out), "--lower", "33",
+                        "--upper", "40", "--seed", "5"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    levels = sorted(int(f.stem) for f in out.glob("*.json"))
+    assert levels == [33, 34, 35, 37, 38, 39]
+    doc = batch.load_result(out / "37.json")
+    assert doc["job"]["seed"] == 5 and doc["job"]["ramified_primes"] == [37] and doc["job"]["eigenvalues_upto"] == 7
+    assert doc["rational_eigenvectors_count"] == 2
+    assert sorted(tuple(v["aps"][p] for p in (2, 3, 5, 7)) for v in doc["rational_eigenvectors"]) == \
+        sorted(tuple(trace_of_frobenius(c, p) for p in (2, 3, 5, 7)) for c in CURVES[37])
+    doc = batch.load_result(out / "38.json")          # 2 * 19: ramified [2], the search keeps oldforms (as the reference's script does)
+    assert doc["job"]["ramified_primes"] == [2] and doc["job"]["unramified_primes"] == [19]
+    assert doc["dimension_total"] == sum(doc["dimensions_by_conductor"].values())
