@@ -298,7 +298,8 @@ struct tb_hecke {
     std::vector<int> rows, rowfirst, rowbase;
     std::vector<int64_t> nnz, nnzbase;
     PoolBuf<int> d_indptr, d_data, d_indices;
-    bool wide_valid = true;            // d_data / d_indices hold the result (else only the narrow twins do)
+    bool wide_valid = true;            // d_data / d_indices hold the result (else only the narrow twins do,
+    std::vector<char> wide_k;          //   and conductor k's int32 arrays exist once wide_k[k] is set)
     int64_t extent = 0;                // entries spanned by the per-conductor regions
     PoolBuf<unsigned short> d_idx16;   // narrow twins of d_indices / d_data written by the row kernel:
     PoolBuf<signed char> d_dat8;       //   3 bytes per entry for the read-back over PCIe
@@ -1369,24 +1370,28 @@ static void copier_destroy(Copier *c)
 
 // int32 arrays for device consumers (device-pointer copies, dense rows, small matrices) of a result
 // that exists in narrow form only.
-static int ensure_wide(tb_hecke *h)
+static int ensure_wide(tb_hecke *h, int64_t k)
 {
     if (h->wide_valid) return TB_OK;
     cudaStream_t st = h->g->stream;
-    TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(h->extent, 1), st));
-    TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(h->extent, 1), st));
-    for (int k = 0; k < h->C; ++k)
+    if (h->wide_k.empty())
     {
-        const size_t n = (size_t)h->nnz[k];
-        if (!n) continue;
+        h->wide_k.assign(h->C, 0);
+        TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(h->extent, 1), st));
+        TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(h->extent, 1), st));
+    }
+    if (h->wide_k[k]) return TB_OK;
+    const size_t n = (size_t)h->nnz[k];
+    if (n)
+    {
         const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
         widen_device_kernel<<<blocks, 256, 0, st>>>(h->d_idx16.ptr + h->nnzbase[k], h->d_dat8.ptr + h->nnzbase[k], n,
                                                     h->d_indices.ptr + h->nnzbase[k], h->d_data.ptr + h->nnzbase[k]);
         ++g_launches;
+        TB_CUDA(cudaGetLastError());
+        TB_CUDA(cudaStreamSynchronize(st));
     }
-    TB_CUDA(cudaGetLastError());
-    TB_CUDA(cudaStreamSynchronize(st));
-    h->wide_valid = true;
+    h->wide_k[k] = 1;
     return TB_OK;
 }
 
@@ -1465,7 +1470,7 @@ extern "C" int tb_hecke_copy_sparse_async(tb_hecke *h, int64_t k, int32_t *data,
     }
     else
     {
-        if (int rc = ensure_wide(h)) return rc;
+        if (int rc = ensure_wide(h, k)) return rc;
         if (nnz && data) TB_CUDA(cudaMemcpyAsync(data, h->d_data.ptr + h->nnzbase[k], nnz * sizeof(int), cudaMemcpyDefault, st));
         if (nnz && indices) TB_CUDA(cudaMemcpyAsync(indices, h->d_indices.ptr + h->nnzbase[k], nnz * sizeof(int), cudaMemcpyDefault, st));
     }
@@ -1487,7 +1492,7 @@ extern "C" int tb_hecke_copy_sparse(tb_hecke *h, int64_t k, int32_t *data, int32
     }
     else
     {
-        if (int rc = ensure_wide(h)) return rc;
+        if (int rc = ensure_wide(h, k)) return rc;
         if (nnz && data) if (int rc = copy_out(h->g, data, h->d_data.ptr + h->nnzbase[k], nnz * sizeof(int))) return rc;
         if (nnz && indices) if (int rc = copy_out(h->g, indices, h->d_indices.ptr + h->nnzbase[k], nnz * sizeof(int))) return rc;
     }
@@ -1606,7 +1611,7 @@ extern "C" int tb_hecke_copy_dense(tb_hecke *h, int64_t k, int32_t *matrix)
     const int dim = (int)h->g->dims[k];
     const size_t cells = (size_t)rows * dim;
     if (cells == 0) return TB_OK;
-    if (int rc = ensure_wide(h)) return rc;
+    if (int rc = ensure_wide(h, k)) return rc;
     cudaPointerAttributes attr;
     bool on_device = cudaPointerGetAttributes(&attr, matrix) == cudaSuccess &&
                      (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
