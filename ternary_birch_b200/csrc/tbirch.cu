@@ -1395,10 +1395,42 @@ static int ensure_wide(tb_hecke *h, int64_t k)
     return TB_OK;
 }
 
+// The narrow read-back only pays where the host can widen faster than PCIe delivers plain int32
+// (~55 GB/s): measured once per process on 16 M entries with the pool (a few tens of ms).
+static bool host_widens_fast_enough()
+{
+    static const bool ok = [] {
+        if (getenv("TBIRCH_FORCE_NARROW_COPY")) return true;
+        const size_t n = (size_t)16 << 20;
+        unsigned short *idx = (unsigned short *)aligned_alloc(64, n * 2);
+        signed char *dat = (signed char *)aligned_alloc(64, n);
+        int32_t *oi = (int32_t *)aligned_alloc(64, n * 4), *od = (int32_t *)aligned_alloc(64, n * 4);
+        bool fast = false;
+        if (idx && dat && oi && od)
+        {
+            memset(idx, 1, n * 2); memset(dat, 1, n); memset(oi, 0, n * 4); memset(od, 0, n * 4);   // fault the pages in first
+            double best = 0;
+            for (int rep = 0; rep < 3; ++rep)
+            {
+                const WidenJob job{idx, dat, oi, od, n};
+                const auto t0 = std::chrono::steady_clock::now();
+                widen_run(job);
+                const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                best = std::max(best, (double)n * 8.0 / sec / 1e9);
+            }
+            fast = best >= 70.0;
+        }
+        free(idx); free(dat); free(oi); free(od);
+        return fast;
+    }();
+    return ok;
+}
+
 static bool narrow_applies(const tb_hecke *h, int64_t k, const int32_t *data, const int32_t *indices)
 {
     return h->d_idx16.ptr && h->maxmult <= 127 && h->nnz[k] >= h->g->narrow_min_nnz &&
-           (data || indices) && host_pointer(data) && host_pointer(indices);
+           (data || indices) && host_pointer(data) && host_pointer(indices) &&
+           (h->g->narrow_min_nnz < (1 << 18) || host_widens_fast_enough());
 }
 
 // data / indices of conductor k -> host arrays through the 3-byte format.  Returns at once;
@@ -1599,7 +1631,8 @@ extern "C" int tb_host_widen_probe(int64_t entries, double *out_gbps, int *threa
 extern "C" int64_t tb_hecke_transfer_bytes(const tb_hecke *h, int64_t k)
 {
     if (!h || k < 0 || k >= h->C) return 0;
-    const bool narrow = h->d_idx16.ptr && h->maxmult <= 127 && h->nnz[k] >= h->g->narrow_min_nnz;
+    const bool narrow = h->d_idx16.ptr && h->maxmult <= 127 && h->nnz[k] >= h->g->narrow_min_nnz &&
+                        (h->g->narrow_min_nnz < (1 << 18) || host_widens_fast_enough());
     return h->nnz[k] * (narrow ? 3 : 8) + ((int64_t)h->rows[k] + 1) * 4;
 }
 
