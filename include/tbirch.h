@@ -120,7 +120,7 @@ int tb_hecke_copy_sparse(tb_hecke *h, int64_t k, int32_t *data, int32_t *indices
  * (tb_hecke_rows(h, k) + 1)-blocks.  Same values as 2^K tb_hecke_copy_sparse calls, a fraction
  * of their fixed costs. */
 int tb_hecke_copy_sparse_all(tb_hecke *h, int32_t *data_all, int32_t *indices_all, int32_t *indptr_all);
-/* Same copy without synchronising: lets the caller overlap the read-back of one T_p with the
+/* tb_hecke_copy_sparse without synchronising: lets the caller overlap the read-back of one T_p with the
  * next one.  Device destinations and small matrices are enqueued on `cuda_stream`; large host
  * destinations are served by the library's background read-back.  Either way
  * tb_hecke_copy_wait(h) is the completion point. */
