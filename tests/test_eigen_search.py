@@ -86,6 +86,75 @@ def test_rational_kernel_lifting_cpu():
         assert verify(v) and eigen.normalize_vector(v) == v
 
 
+def numpy_kernel_mod(M, P):
+    """Vectorised reference elimination for the CPU test of the search logic (residues < 2^29, so
+    products fit int64)."""
+    M = np.array(M, dtype=np.int64) % P
+    rows, cols = M.shape
+    pivots, r = [], 0
+    for c in range(cols):
+        nz = np.nonzero(M[r:, c])[0]
+        if len(nz) == 0:
+            continue
+        piv = r + int(nz[0])
+        if piv != r:
+            M[[r, piv]] = M[[piv, r]]
+        M[r] = (M[r] * pow(int(M[r, c]), P - 2, P)) % P
+        f = M[:, c].copy()
+        f[r] = 0
+        M = (M - f[:, None] * M[r][None, :]) % P
+        pivots.append(c)
+        r += 1
+        if r == rows:
+            break
+    free = [c for c in range(cols) if c not in pivots]
+    basis = np.zeros((len(free), cols), dtype=np.uint32)
+    for k, fc in enumerate(free):
+        basis[k, fc] = 1
+        for i, pc in enumerate(pivots):
+            basis[k, pc] = (-int(M[i, fc])) % P
+    return tuple(free), basis, 0.0
+
+
+def test_search_logic_on_cpu(tables, port_oracle, golden_dir, monkeypatch):
+    """The host side of the search (job queue, Hasse candidates, CRT lift, exact verification,
+    eigenspace splitting, normalisation) with the GPU eliminations replaced by a numpy one and T_p
+    taken from the oracle: level 85085 must give the fixture's vectors."""
+    from scipy.sparse import csr_matrix
+    t = tables("85085")
+    oracle = port_oracle("85085")
+
+    class OracleGenus:
+        dims = {int(c): int(d) for c, d in zip(t.conductors, t.dims)}
+        cache = {}
+
+        def next_good_prime(self, p):
+            while True:
+                p += 1
+                if all(p % d for d in range(2, int(p ** 0.5) + 1)) and 85085 % p:
+                    return p
+
+        def hecke_matrix(self, p, conductor, sparse=None, precise=True):
+            if p not in self.cache:
+                self.cache[p] = {m["conductor"]: csr_matrix((m["data"], m["indices"], m["indptr"]), shape=(m["dim"], m["dim"]))
+                                 for m in oracle.hecke(p, True)}
+            return self.cache[p][conductor]
+
+    monkeypatch.setattr(eigen, "kernel_mod_csr",
+                        lambda data, indices, indptr, n, shift, P: numpy_kernel_mod(
+                            csr_matrix((data, indices, indptr), shape=(n, n)).toarray().astype(np.int64)
+                            - shift * np.eye(n, dtype=np.int64), P))
+    monkeypatch.setattr(eigen, "kernel_mod_dense", lambda M, P: numpy_kernel_mod(M, P))
+    vecs, stats = eigen.rational_eigenvectors(OracleGenus())
+    gold = json.load(open(golden_dir / "eigen_85085.json"))
+    want = {(v["conductor"], tuple(v["vector"])) for v in gold["vectors"] if len(set(v["vector"])) > 1}
+    got = {(v["conductor"], tuple(v["vector"])) for v in vecs}
+    assert got == want and len(vecs) == len(got)
+    assert stats["kernels"] >= 160 and all(2 in v["aps"] for v in vecs)
+    # two of them share a_2 and a_3 and are only separated at p = 19 (pyx:345-375)
+    assert any(19 in v["aps"] for v in vecs)
+
+
 def random_matrix(rng, rows, cols, rank, P):
     a = [[rng.randrange(P) for _ in range(rank)] for _ in range(rows)]
     b = [[rng.randrange(P) for _ in range(cols)] for _ in range(rank)]
