@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TBIRCH_ABI_VERSION 1
+#define TBIRCH_ABI_VERSION 2
 
 typedef enum tb_status {
     TB_OK = 0,

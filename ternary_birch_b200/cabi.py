@@ -99,7 +99,7 @@ def lib() -> ctypes.CDLL:
     L.tb_table_desc.argtypes = [vp, ctypes.POINTER(GenusDesc), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
     L.tb_table_destroy.argtypes = [vp]
     L.tb_table_destroy.restype = None
-    if L.tb_abi_version() != 1:
+    if L.tb_abi_version() != 2:
         raise RuntimeError("libtbirch.so ABI version mismatch")
     _lib = L
     return L
