@@ -315,6 +315,8 @@ struct RowLaunch {
     int *ticket;           // row dispenser, zeroed before launch (FUSED)
     i64 *nnz_out;          // [2^K] written by the last row (FUSED)
     int *maxmult;          // max number of neighbors of one row in one class = max |entry| (narrow read-back)
+    u32 *scratch;          // global-memory stand-in for the per-row shared-memory state when it does not fit one SM:
+    size_t scratch_words;  //   one slot of scratch_words per CTA, and each CTA then walks several rows
     unsigned short *idx16; // optional narrow twins of indices / data for the read-back over PCIe
     signed char *dat8;     //   (valid when every dim <= 65536 and maxmult <= 127), same offsets
     int *data;
@@ -323,14 +325,16 @@ struct RowLaunch {
 
 enum { ROWS_COUNT = 0, ROWS_FILL = 1, ROWS_FUSED = 2 };
 
-template <int MODE>
+template <int MODE, bool SCRATCH = false>
 __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ RowLaunch L)
 {
     extern __shared__ u32 smem[];
     // layout: mask[mw] | wprefix[mw] | start[maxcols+1] | colr[maxcols] | scratch[256] | spins (u16)[P1]
+    // (in shared memory; for a very large genus at a very large prime the same layout lives in a
+    //  per-CTA slot of global memory and the CTA walks rows persistently)
     const int mw = L.mask_words;
     const int maxcols = min((int)L.P1, L.N);
-    u32 *mask = smem;
+    u32 *mask = SCRATCH ? L.scratch + (size_t)blockIdx.x * L.scratch_words : smem;
     u32 *wprefix = mask + mw;
     int *start = (int *)(wprefix + mw);
     int *colr = start + maxcols + 1;
@@ -339,6 +343,8 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
 
     __shared__ int s_row;
     __shared__ i64 s_base[8];
+    for (int walk = 0;; ++walk)
+    {
     if (MODE == ROWS_FUSED)
     {
         // tickets are handed out in launch order, so every row a CTA waits on below belongs
@@ -346,7 +352,8 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
         if (threadIdx.x == 0) s_row = atomicAdd(L.ticket, 1);
         __syncthreads();
     }
-    const int lrow = MODE == ROWS_FUSED ? s_row : (int)blockIdx.x;
+    const int lrow = MODE == ROWS_FUSED ? s_row : (int)(blockIdx.x + (size_t)walk * gridDim.x);
+    if (lrow >= L.rows) break;
     const int n = L.rep_begin + lrow;
     const u32 *Wrow = L.W + (size_t)lrow * L.P1;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -621,6 +628,9 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
                 }
             }
         }
+    }
+    if (!SCRATCH) break;         // shared-memory form: one row per CTA
+    __syncthreads();
     }
 }
 

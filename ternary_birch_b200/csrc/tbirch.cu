@@ -261,6 +261,7 @@ struct tb_genus {
     DevBuf<i64> d_nnz;          // nnz | nnzbase
     DevBuf<u64> d_lookback;     // [2^K][rows] look-back words + ticket (fused row kernel)
     DevBuf<int> d_maxmult;      // [1] largest |entry| bound of the last T_p (narrow read-back)
+    DevBuf<u32> d_rowscratch;   // row-kernel state in global memory when it does not fit shared memory
     int *h_maxmult = nullptr;   // pinned [1]
     struct Copier *copier = nullptr;   // background thread of the narrow read-back (started on first use)
     bool allow_narrow = true;     // TBIRCH_NO_NARROW_COPY turns the compressed read-back off
@@ -533,6 +534,7 @@ extern "C" void tb_genus_destroy(tb_genus *g)
     if (g->h_nnz) cudaFreeHost(g->h_nnz);
     if (g->h_maxmult) cudaFreeHost(g->h_maxmult);
     g->d_maxmult.release();
+    g->d_rowscratch.release();
     copier_destroy(g->copier);
     g->copier = nullptr;
     if (g->h_tab) cudaFreeHost(g->h_tab);
@@ -881,9 +883,21 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     R.nnz_out = d_nnz.ptr;
     R.maxmult = g->d_maxmult.ptr;
     TB_CUDA(cudaMemsetAsync(g->d_maxmult.ptr, 0, sizeof(int), g->stream));
-    const size_t smem = rows_smem_bytes(N, P1);
-    if (smem > 218 * 1024)
-        return fail(TB_ERR_RUNTIME, "libtbirch: row accumulation needs more shared memory than one SM has for this (N, p)");
+    size_t smem = rows_smem_bytes(N, P1);
+    unsigned row_grid = (unsigned)rows;
+    if (smem > 218 * 1024 || getenv("TBIRCH_ROWS_SCRATCH"))
+    {
+        // the row's sort state does not fit one SM (a genus of > 20000 classes at p > 30000): keep it in a
+        // global-memory slot per CTA and let two CTAs per SM walk the rows
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        row_grid = (unsigned)std::min<int>(rows, 2 * sms);
+        R.scratch_words = (smem + 3) / 4;
+        TB_CUDA(g->d_rowscratch.reserve(R.scratch_words * row_grid));
+        R.scratch = g->d_rowscratch.ptr;
+        smem = 0;
+    }
     const int threads = (int)std::min<u32>(512, std::max<u32>(64, (P1 + 31) / 32 * 32));
     static bool attrs_set = false;
     if (!attrs_set)
@@ -927,7 +941,8 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
         TB_CUDA(cudaMemcpyAsync(d_nnz.ptr + C, g->h_nnz + C, C * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
         R.lookback = g->d_lookback.ptr;
         R.ticket = (int *)(g->d_lookback.ptr + (size_t)C * rows);
-        rows_kernel<ROWS_FUSED><<<rows, threads, smem, g->stream>>>(R);
+        if (R.scratch) rows_kernel<ROWS_FUSED, true><<<row_grid, threads, 0, g->stream>>>(R);
+        else rows_kernel<ROWS_FUSED><<<row_grid, threads, smem, g->stream>>>(R);
         ++g_launches;
         TB_CUDA(cudaGetLastError());
         TB_CUDA(cudaEventRecord(g->ev2, g->stream));
@@ -947,7 +962,8 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
             R.idx16 = nullptr; R.dat8 = nullptr;
             R.data = h->d_data.ptr; R.indices = h->d_indices.ptr;
             TB_CUDA(cudaMemsetAsync(g->d_lookback.ptr, 0, ((size_t)C * rows + 2) * sizeof(u64), g->stream));
-            rows_kernel<ROWS_FUSED><<<rows, threads, smem, g->stream>>>(R);
+            if (R.scratch) rows_kernel<ROWS_FUSED, true><<<row_grid, threads, 0, g->stream>>>(R);
+            else rows_kernel<ROWS_FUSED><<<row_grid, threads, smem, g->stream>>>(R);
             ++g_launches;
             TB_CUDA(cudaGetLastError());
             TB_CUDA(cudaEventRecord(g->ev2, g->stream));
@@ -957,7 +973,8 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     }
     else
     {
-        rows_kernel<ROWS_COUNT><<<rows, threads, smem, g->stream>>>(R);
+        if (R.scratch) rows_kernel<ROWS_COUNT, true><<<row_grid, threads, 0, g->stream>>>(R);
+        else rows_kernel<ROWS_COUNT><<<row_grid, threads, smem, g->stream>>>(R);
         ++g_launches;
         TB_CUDA(cudaGetLastError());
         indptr_scan_kernel<<<C, 256, 0, g->stream>>>(h->d_indptr.ptr, d_tab.ptr, d_tab.ptr + 2 * C, d_nnz.ptr);
@@ -990,7 +1007,8 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
         }
         for (int k = 0; k < C; ++k) g->h_nnz[C + k] = h->nnzbase[k];
         TB_CUDA(cudaMemcpyAsync(d_nnz.ptr + C, g->h_nnz + C, C * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
-        rows_kernel<ROWS_FILL><<<rows, threads, smem, g->stream>>>(R);
+        if (R.scratch) rows_kernel<ROWS_FILL, true><<<row_grid, threads, 0, g->stream>>>(R);
+        else rows_kernel<ROWS_FILL><<<row_grid, threads, smem, g->stream>>>(R);
         ++g_launches;
         TB_CUDA(cudaGetLastError());
         TB_CUDA(cudaEventRecord(g->ev2, g->stream));

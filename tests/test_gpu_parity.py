@@ -372,15 +372,19 @@ def test_narrow_readback_matches_plain(tables, monkeypatch, name, p, want_narrow
 
 
 @pytest.mark.parametrize("env", [dict(TBIRCH_TWO_PASS_ROWS="1"), dict(TBIRCH_TWO_PASS_ROWS="1", TBIRCH_NARROW_MIN_NNZ="1"),
+                                 dict(TBIRCH_ROWS_SCRATCH="1"), dict(TBIRCH_ROWS_SCRATCH="1", TBIRCH_TWO_PASS_ROWS="1"),
                                  dict(TBIRCH_NARROW_MIN_NNZ="1", TBIRCH_NARROW_MAX_RATIO="100000"),
                                  dict(TBIRCH_TWO_PASS_ROWS="1", TBIRCH_NARROW_MIN_NNZ="1", TBIRCH_NARROW_MAX_RATIO="100000")])
 def test_row_kernel_variants_agree(tables, port_oracle, monkeypatch, env):
     """The row phase has a fused single-pass form and a count/scan/fill form, each with int32 or narrow
     output.  With the narrow attempt forced at p = 16381 >> N = 130 an entry exceeds 8 bits, so the fused form
     must redo the row pass in int32 and the two-pass form must pick int32 after its count pass.  All variants
-    equal the oracle."""
+    equal the oracle.  TBIRCH_ROWS_SCRATCH forces the form the kernel takes when a row's sort state exceeds
+    one SM's shared memory (more than ~20000 classes at p > ~30000): the state in a global-memory slot per
+    CTA, CTAs walking the rows persistently."""
     from ternary_birch_b200 import Genus
-    for k in ("TBIRCH_TWO_PASS_ROWS", "TBIRCH_NARROW_MIN_NNZ", "TBIRCH_NARROW_MAX_RATIO", "TBIRCH_NO_NARROW_COPY"):
+    for k in ("TBIRCH_TWO_PASS_ROWS", "TBIRCH_NARROW_MIN_NNZ", "TBIRCH_NARROW_MAX_RATIO", "TBIRCH_NO_NARROW_COPY",
+              "TBIRCH_ROWS_SCRATCH"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -400,5 +404,23 @@ def test_row_kernel_variants_agree(tables, port_oracle, monkeypatch, env):
             assert np.array_equal(dense0, want), (env, p)
             if p == 16381:
                 assert np.abs(data).max() > 127          # the case the int32 fallback exists for
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("two_pass", [False, True])
+def test_row_kernel_global_scratch_walks_rows(tables, port_oracle, monkeypatch, two_pass):
+    """The global-memory form of the row kernel with more rows (2016) than resident CTAs (296), so every
+    CTA walks several rows and the look-back chains across walks."""
+    from ternary_birch_b200 import Genus
+    monkeypatch.setenv("TBIRCH_ROWS_SCRATCH", "1")
+    if two_pass:
+        monkeypatch.setenv("TBIRCH_TWO_PASS_ROWS", "1")
+    else:
+        monkeypatch.delenv("TBIRCH_TWO_PASS_ROWS", raising=False)
+    g = Genus(tables("1062347"), precise=False)
+    try:
+        for p in (3, 101):
+            assert_same_csr(g.hecke_matrix_sparse(p), port_oracle("1062347").hecke(p, False), (two_pass, p))
     finally:
         g.close()
