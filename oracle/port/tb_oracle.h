@@ -5,7 +5,7 @@
  * CUDA path: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load it.  The product never links or calls it.
  *
- * Parity status: PINNED.  tests/test_oracle_port.py checks every function here
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks every function here
  * bit-for-bit against outputs of the unmodified reference compiled into
  * oracle/_ref/birch_ref (fixtures under tests/golden/, generator
  * tests/golden/make_golden.py).
