@@ -335,9 +335,7 @@ def main():
         pending[slot] = (res, ev)
 
     # warm-up: W untimed steps, at least six: both pinned result sets must have been written by the host
-    # once (the first CPU store to a page of a fresh cudaHostAlloc mapping takes a minor fault), and with
-    # several ranks per host the first few read-backs run at half speed (8 GPUs: 460 ms per step for four
-    # steps, then 196 ms)
+    # once (the first CPU store to a page of a fresh cudaHostAlloc mapping takes a minor fault)
     for i in range(max(6, args.warmup)):
         step_e2e(i)
     drain(0)
