@@ -148,10 +148,10 @@ static int copy_out(tb_genus *g, void *dst, const void *src_dev, size_t bytes)
 // Narrow read-back.  A T_p at the bench size is 3.6 GB of int32 CSR; PCIe moves it at
 // ~54 GB/s, three times longer than the GPU needs to compute it.  When every column index
 // fits 16 bits and every |entry| fits 8 (known from the row kernel's max-multiplicity word),
-// the device packs indices/entries to 3 bytes per entry, the DMA moves those into pinned
+// the row kernel writes indices/entries as 3 bytes per entry, the DMA moves those into pinned
 // staging, and host threads widen them into the caller's int32 arrays with streaming stores.
-// Two internal streams alternate chunks so the DMA of one chunk overlaps the widening of
-// the previous one; the caller's stream waits on both.
+// A background thread per genus (Copier, below) keeps two chunk DMAs in flight while the
+// previous chunk is widened; tb_hecke_copy_wait observes completion.
 // ---------------------------------------------------------------------------
 static size_t narrow_chunk_entries()
 {
