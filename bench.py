@@ -174,6 +174,36 @@ def run_reference_arm(args):
     return 0
 
 
+def host_ingest_summary(per_rank, csr_bytes_per_neighbor, e2e_value):
+    """The two ceilings of delivering int32 CSR into this host's memory, measured with all ranks
+    active at once right after the end-to-end loop: plain DMA into pinned memory, and the host
+    threads' streaming stores (the widening path).  End to end cannot beat the larger one."""
+    dma = [r["ingest"]["dma_gbs"] for r in per_rank]
+    wid = [r["ingest"]["widen_gbs"] for r in per_rank]
+    c_dma = sum(dma) * 1e9 / csr_bytes_per_neighbor
+    c_wid = sum(wid) * 1e9 / csr_bytes_per_neighbor
+    # weak scaling is timed as the max over ranks: with plain DMA the slowest link sets the step
+    c_dma_slowest = len(dma) * min(dma) * 1e9 / csr_bytes_per_neighbor
+    return dict(csr_bytes_per_neighbor=round(csr_bytes_per_neighbor, 2), dma_gbs_per_rank=dma, dma_gbs_total=round(sum(dma), 1),
+                widen_gbs_per_rank=wid, widen_gbs_total=round(sum(wid), 1), widen_threads_per_rank=per_rank[0]["ingest"]["widen_threads"],
+                ceiling_dma_neighbors_per_s=c_dma, ceiling_dma_slowest_rank_neighbors_per_s=c_dma_slowest,
+                ceiling_widen_neighbors_per_s=c_wid, e2e_frac_of_ceiling=e2e_value / max(c_dma, c_wid),
+                note="all ranks concurrently; see profiles/r2a_d2h_probe_n4.md")
+
+
+def fullsize_note(cores, sampled_total):
+    """The sampled reference rate next to the one full-size timing committed under profiles/."""
+    f = ROOT / "profiles" / "r2_reference_fullsize.json"
+    if not f.exists():
+        return ""
+    try:
+        rec = json.load(open(f))
+        return (f"; sampled {sampled_total / cores / 1e6:.2f} M neighbors/s/core here vs {rec['neighbors_per_s_per_core'] / 1e6:.2f} M/s/core "
+                f"at full size ({rec['what']})")
+    except Exception:
+        return ""
+
+
 def bind_to_gpu_numa_node(torch, local_rank: int):
     """Best effort: run this rank (and so its pinned-memory allocations, first touch) on the CPUs of
     the NUMA node its GPU hangs off, so the end-to-end copies of 8 ranks do not cross sockets."""
@@ -212,6 +242,8 @@ def main():
 
     if args.impl == "reference":
         return run_reference_arm(args)
+
+    import ctypes
 
     import numpy as np
     import torch
@@ -360,39 +392,84 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total_neighbors / (float(t.item()) * 1e-3)
+    my_steps = [round((b - a) * 1e3, 1) for a, b in zip(step_marks, step_marks[1:])]
+    pol = [ctypes.c_double(), ctypes.c_double(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()]
+    cabi.check(L.tb_readback_stats(*[ctypes.byref(x) for x in pol]))
+    my_policy = dict(rank=rank, format="narrow" if pol[4].value else "plain", plain_gbs=round(pol[0].value, 1),
+                     narrow_gbs=round(pol[1].value, 1), plain_samples=pol[2].value, narrow_samples=pol[3].value)
 
-    # ---- final integer gather of the Hecke rows (once, untimed region) -------
-    gather_ms = None
+    # ---- what can this host ingest?  All ranks at once: plain DMA into pinned memory, then the
+    # widening threads alone (profiles/r2a_d2h_probe_n4.md explains why these are the two ceilings).
+    probe_src = flush[:256 << 20]
+    probe_dst = pinned[0][0][0].view(torch.uint8)
+    probe_len = min(probe_src.numel(), probe_dst.numel()) // 4096 * 4096
+    sync_all()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 12
+    pe0.record(stream)
+    for _ in range(reps):
+        probe_dst[:probe_len].copy_(probe_src[:probe_len], non_blocking=True)
+    pe1.record(stream)
+    torch.cuda.synchronize()
+    my_dma = reps * probe_len / (pe0.elapsed_time(pe1) * 1e-3) / 1e9
+    sync_all()
+    wg, wt, wi = ctypes.c_double(), ctypes.c_int(), ctypes.c_int()
+    cabi.check(L.tb_host_widen_probe(16 << 20, ctypes.byref(wg), ctypes.byref(wt), ctypes.byref(wi)))
+    my_ingest = dict(rank=rank, dma_gbs=round(my_dma, 1), widen_gbs=round(wg.value, 1), widen_threads=wt.value)
+    per_rank = [dict(steps=my_steps, policy=my_policy, ingest=my_ingest)]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, dict(steps=my_steps, policy=my_policy, ingest=my_ingest))
+
+    # ---- final integer gather of the Hecke rows (once, outside the timed region) -------
+    gather = None
     if world > 1:
         res = g.hecke_device(p)
-        torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
-        got = shard.gather_hecke_device(res, dev)
-        torch.cuda.synchronize()
-        gather_ms = (time.perf_counter() - t0) * 1e3
+        shard.warm_gather(dev)                       # NCCL point-to-point connection set-up, once
+        gms = []
+        for _ in range(2):
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            got = shard.gather_hecke_device(res, dev)
+            torch.cuda.synchronize()
+            gms.append((time.perf_counter() - t0) * 1e3)
+        t = torch.tensor(gms, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
-            headers, payloads = got
-            assert len(payloads) == world and all(int(h[0]) == C for h in headers)
-            # rank 0's own rows must come back unchanged: conductor-1 data sums to (p+1) * dim
-            nnz0 = int(headers[0][2])
-            assert int(payloads[0][:nnz0].sum().item()) == (p + 1) * N
+            parts, info = got
+            assert len(parts) == world
+            for r, part in enumerate(parts):
+                # every rank's rows must arrive intact: conductor 1 has no character, so its entries
+                # count neighbors and sum to (p_r + 1) * N; every indptr ends at its nnz
+                pr = PRIMES_DESC[r % len(PRIMES_DESC)]
+                data, indices, indptr = part[1]
+                assert int(data.sum(dtype=torch.int64).item()) == (pr + 1) * N, f"gathered rows of rank {r} are damaged"
+                assert int(indptr[-1].item()) == data.numel() and int(indices.max().item()) < N
+                for cond, (d_, i_, ptr_) in part.items():
+                    assert int(ptr_[-1].item()) == d_.numel() == i_.numel(), (r, cond)
+            gather = dict(ms=float(t[1].item()), first_call_ms=float(t[0].item()), bytes_over_nvlink=int(sum(info["bytes_per_rank"][1:])),
+                          entry_bytes=info["entry_bytes"], verified_ranks=world,
+                          how="tb_hecke_pack (3-byte form) -> one all_gather of sizes -> grouped send/recv to rank 0 "
+                              "-> tb_unpack_rows (int32 CSR on rank 0's device)")
+            del parts, got
         res.close()
 
     # ---- roofline of the dominant kernel (neighbors_kernel) ------------------
     peak = None
     if rank == 0:
-        import ctypes
-        a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
-        cabi.check(L.tb_int_peak(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
-        peak = dict(imad=a.value, alu=b.value, mixed=c.value)
+        arms = (ctypes.c_double * 5)()
+        cabi.check(L.tb_int_peak_detail(arms))
+        peak = dict(imad_only=arms[0], lop3_only=arms[1], add_only=arms[2], imad_add=arms[3], imad_lop3=arms[4])
     kms = sorted(kernel_ms)[len(kernel_ms) // 2]
     rms = sorted(rows_ms)[len(rows_ms) // 2]
 
     if rank == 0:
         w32 = int32_ops_per_neighbor(p, K)
         achieved = neighbors_per_step * w32 / (kms * 1e-3) / 1e12
-        measured_peak = max(peak["mixed"], peak["imad"], peak["alu"]) / 1e12
+        measured_peak = max(peak.values()) / 1e12
+        sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+        nominal_peak = torch.cuda.get_device_properties(dev).multi_processor_count * 4 * 32 * sm_mhz * 1e6 / 1e12
         peaks_file = ROOT / "MEASURED_PEAKS.json"
         hbm_peak = json.load(open(peaks_file))["hbm_gbs"] if peaks_file.exists() else 6650.0
         # algorithmic DRAM-side bytes per neighbor: the 4-byte packed word written, plus the packed
@@ -403,10 +480,13 @@ def main():
         if tf.exists():
             traffic = json.load(open(tf)).get("dram_bytes_per_launch")
         roofline = dict(bound="int32-issue", achieved=achieved, peak=measured_peak, unit="Tint32op/s",
-                        frac=achieved / measured_peak, traffic=traffic,
+                        frac=achieved / measured_peak, frac_of_nominal_issue=achieved / nominal_peak,
+                        nominal_issue_peak=nominal_peak, traffic=traffic,
                         kernel="neighbors_kernel<%s,PACKED>" % {"int64-wrap": "W64", "int64-bounded": "X64", "int128-bounded": "U128", "int128-checked": "C128"}[g.last_int_mode()], kernel_ms=kms, rows_kernels_ms=rms,
-                        int32_ops_per_neighbor=w32, peak_source="tb_int_peak microbenchmark, measured in this run "
-                        "(IMAD/IADD3+LOP3 chains on all SMs)", peak_detail=peak,
+                        int32_ops_per_neighbor=w32, peak_source="tb_int_peak_detail microbenchmark, measured in this run: best of five "
+                        "arms of single-SASS-instruction chains on all SMs, operations counted per instruction; "
+                        "nominal = SMs x 4 schedulers x 32 lanes x SM clock (one warp instruction per scheduler per clock)",
+                        peak_detail=peak,
                         hbm=dict(achieved=hbm_achieved, peak=hbm_peak, unit="GB/s", frac=hbm_achieved / hbm_peak,
                                  peak_source="MEASURED_PEAKS.json" if peaks_file.exists() else "fallback"))
         cpu = None
@@ -416,7 +496,8 @@ def main():
             n, s, kind = reference_sample(primes, precise=args.precise)
             cpu = dict(value=n / s, unit=UNIT, cores=len(primes), kind=kind,
                        sample=f"same genus, Genus::hecke_matrix_sparse(p) {'GMP' if args.precise else 'int64'} for the "
-                              f"{len(primes)} primes {primes[0]}..{primes[-1]}, one process per prime; {s:.1f} s wall")
+                              f"{len(primes)} primes {primes[0]}..{primes[-1]}, one process per prime; {s:.1f} s wall"
+                              + fullsize_note(len(primes), n / s))
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype=g.last_int_mode() if args.precise else "int64", data="synthetic",
@@ -427,10 +508,14 @@ def main():
                     roofline=roofline, cpu_baseline=cpu,
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
                              result_bytes_per_step=result_bytes,
-                             step_wall_ms=[round((b - a) * 1e3, 1) for a, b in zip(step_marks, step_marks[1:])],
-                             readback="uint16 column + int8 entry over PCIe, widened to the reference's int32 CSR by host threads" if d2h_bytes < result_bytes else "int32 CSR over PCIe"),
+                             step_wall_ms=my_steps,
+                             slowest_rank_step_wall_ms=max((r["steps"] for r in per_rank), key=lambda v: sum(v[:-1])),
+                             readback="per rank, chosen from measured delivery rates (tb_readback_stats): uint16 column + int8 "
+                                      "entry over PCIe widened to the reference's int32 CSR by host threads, or int32 CSR over PCIe",
+                             readback_policy=[r["policy"] for r in per_rank],
+                             host_ingest=host_ingest_summary(per_rank, result_bytes / neighbors_per_step, e2e_value)),
                     gpu_launches=int(launches_timed), clocks=clocks, numa_node=numa_node, T_p_wall_ms=total_ms / args.steps,
-                    final_gather_ms=gather_ms)
+                    final_gather_ms=(gather or {}).get("ms"), final_gather=gather)
         print(json.dumps(line), flush=True)
     g.close()
     if world > 1:

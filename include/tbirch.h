@@ -135,10 +135,32 @@ int tb_hecke_copy_wait(tb_hecke *h);
  * through a 3-byte-per-entry device format (uint16 column, int8 entry) that the library widens
  * on the host; the arrays the caller receives are the reference's int32 CSR either way. */
 int64_t tb_hecke_transfer_bytes(const tb_hecke *h, int64_t k);
+/* Which of the two read-back formats large host copies use is decided per rank from measured
+ * delivery rates (profiles/r2a_d2h_probe_n4.md: what a rank gets depends on the host and on the
+ * other ranks): running GB/s of delivered int32 CSR for the plain DMA and for the 3-byte format,
+ * the number of large read-backs behind each figure, and the format currently preferred
+ * (0 plain, 1 narrow).  TBIRCH_NO_NARROW_COPY / TBIRCH_FORCE_NARROW_COPY pin the choice. */
+int tb_readback_stats(double *plain_gbps, double *narrow_gbps, int *plain_samples, int *narrow_samples,
+                      int *current);
 /* Host-side widening throughput of this machine (no GPU involved; diagnostic): output GB/s of the
  * library's thread pool on `entries` packed entries, the pool size, and whether the AVX2
  * streaming-store path is in use. */
 int tb_host_widen_probe(int64_t entries, double *out_gbps, int *threads, int *avx2);
+
+/* ---- final integer gather of the rows (multi-GPU) ---------- */
+/* The path needs no collective until the end: rank i holds the rows (or the primes) it computed.
+ * tb_hecke_pack lays ALL conductors of `h` out in one device buffer of tb_hecke_packed_bytes(h)
+ * bytes -- per conductor: columns[nnz] | entries[nnz] | indptr[rows + 1], each section padded to
+ * 16 bytes; *entry_bytes = 3: uint16 columns + int8 entries, 8: int32 + int32 (a column or an
+ * entry does not fit) -- which the caller ships to the root with grouped send/recv
+ * (ternary_birch_b200/shard.py does it over torch.distributed/NCCL, unpadded).  On the root,
+ * tb_unpack_rows widens one such buffer into the reference's int32 CSR on the device, conductors
+ * back to back (the layout of tb_hecke_copy_sparse_all).  Both enqueue on `cuda_stream`. */
+int64_t tb_hecke_packed_bytes(const tb_hecke *h, int *entry_bytes);
+int tb_hecke_pack(tb_hecke *h, void *dst_device, void *cuda_stream);
+int tb_unpack_rows(const void *packed_device, int entry_bytes, int64_t num_conductors, const int64_t *nnz,
+                   const int64_t *rows, int32_t *data_all, int32_t *indices_all, int32_t *indptr_all,
+                   void *cuda_stream);
 
 /* Row-major rows x dim block, Genus.h:811-846. */
 int tb_hecke_copy_dense(tb_hecke *h, int64_t k, int32_t *matrix);
@@ -222,9 +244,14 @@ float tb_modkernel_ms(const tb_modkernel *k);
 void tb_modkernel_destroy(tb_modkernel *k);
 
 /* ---- integer-pipe microbenchmark -------------------------------------- */
-/* Measures the int32 issue peak used as the roofline denominator: runs an
- * unrolled IMAD + IADD3/LOP3 chain on every SM.  Returns int32 op/s. */
-int tb_int_peak(double *imad_ops_per_s, double *iadd_ops_per_s, double *mixed_ops_per_s);
+/* Measures the int32 issue peak used as the roofline denominator: unrolled chains of single
+ * SASS instructions on every SM, counted per instruction.  Returns int32 op/s for
+ * out[0] IMAD only (fma pipe), out[1] LOP3 only (alu pipe), out[2] ADD only (ptxas splits them
+ * over both pipes), out[3] IMAD + ADD alternating, out[4] IMAD + LOP3 alternating.  The nominal
+ * bound of the two-pipe arms is the issue slot: SMs x 4 x 32 x clock. */
+int tb_int_peak_detail(double out[5]);
+/* The same, condensed: fma-pipe-only, alu-pipe-only, and the best two-pipe arm. */
+int tb_int_peak(double *imad_ops_per_s, double *alu_ops_per_s, double *mixed_ops_per_s);
 
 #ifdef __cplusplus
 }

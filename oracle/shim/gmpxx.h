@@ -7,6 +7,9 @@
 // (mpz_tdiv_q / mpz_tdiv_r), `>>` is an arithmetic (floor) shift.
 #ifndef TB_ORACLE_SHIM_GMPXX_H
 #define TB_ORACLE_SHIM_GMPXX_H
+#ifndef __GMP_PLUSPLUS__
+#define __GMP_PLUSPLUS__ 1          /* what the real gmpxx.h defines; the facade keys IntegerTraits<mpz_class> on it */
+#endif
 
 #include <gmp.h>
 #include <cstdlib>
@@ -38,6 +41,7 @@ public:
     mpz_ptr get_mpz_t() { return v; }
     mpz_srcptr get_mpz_t() const { return v; }
     long get_si() const { return mpz_get_si(v); }
+    bool fits_slong_p() const { return mpz_fits_slong_p(v) != 0; }
     unsigned long get_ui() const { return mpz_get_ui(v); }
     double get_d() const { return mpz_get_d(v); }
     std::string get_str(int base = 10) const

@@ -50,6 +50,11 @@ def lib() -> ctypes.CDLL:
     L.tb_hecke_transfer_bytes.argtypes = [vp, i64]
     L.tb_hecke_transfer_bytes.restype = i64
     L.tb_host_widen_probe.argtypes = [i64, vp, vp, vp]
+    L.tb_readback_stats.argtypes = [vp, vp, vp, vp, vp]
+    L.tb_hecke_packed_bytes.argtypes = [vp, vp]
+    L.tb_hecke_packed_bytes.restype = i64
+    L.tb_hecke_pack.argtypes = [vp, vp, vp]
+    L.tb_unpack_rows.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp]
     L.tb_modkernel_csr.argtypes = [vp, vp, vp, i64, i64, ctypes.c_uint32, vp]
     L.tb_modkernel_dense.argtypes = [vp, i64, i64, ctypes.c_uint32, vp]
     L.tb_modkernel_dim.argtypes = [vp]
@@ -94,6 +99,7 @@ def lib() -> ctypes.CDLL:
     L.tb_isoseq_close.restype = None
     L.tb_neighbor_records.argtypes = [vp, u64, i32, i64, i64, vp]
     L.tb_int_peak.argtypes = [vp, vp, vp]
+    L.tb_int_peak_detail.argtypes = [vp]
     L.tb_quad_form.argtypes = [ctypes.POINTER(PrimeSymbol), i64, vp]
     L.tb_genus_enumerate.argtypes = [vp, ctypes.POINTER(PrimeSymbol), i64, u64, ctypes.POINTER(vp)]
     L.tb_table_desc.argtypes = [vp, ctypes.POINTER(GenusDesc), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
@@ -111,9 +117,9 @@ EXPORTS = [
     "tb_genus_num_conductors", "tb_genus_conductor", "tb_genus_dim",
     "tb_hecke_compute", "tb_hecke_compute_rows", "tb_hecke_num_conductors", "tb_hecke_conductor",
     "tb_hecke_dim", "tb_hecke_rows", "tb_hecke_row_begin", "tb_hecke_nnz", "tb_hecke_copy_sparse",
-    "tb_hecke_copy_sparse_async", "tb_hecke_copy_sparse_all", "tb_hecke_copy_wait", "tb_hecke_transfer_bytes", "tb_host_widen_probe",
+    "tb_hecke_copy_sparse_async", "tb_hecke_copy_sparse_all", "tb_hecke_copy_wait", "tb_hecke_transfer_bytes", "tb_host_widen_probe", "tb_readback_stats", "tb_hecke_packed_bytes", "tb_hecke_pack", "tb_unpack_rows",
     "tb_hecke_copy_dense", "tb_hecke_destroy", "tb_eigenvalues", "tb_isoseq_open", "tb_isoseq_done",
-    "tb_isoseq_next", "tb_isoseq_read", "tb_isoseq_close", "tb_neighbor_records", "tb_int_peak",
+    "tb_isoseq_next", "tb_isoseq_read", "tb_isoseq_close", "tb_neighbor_records", "tb_int_peak", "tb_int_peak_detail",
     "tb_quad_form", "tb_genus_enumerate", "tb_table_desc", "tb_table_destroy",
     "tb_modkernel_csr", "tb_modkernel_dense", "tb_modkernel_dim", "tb_modkernel_cols", "tb_modkernel_free_cols",
     "tb_modkernel_basis", "tb_modkernel_ms", "tb_modkernel_destroy",

@@ -666,6 +666,17 @@ __global__ void widen_device_kernel(const unsigned short *idx16, const signed ch
     }
 }
 
+// The 3-byte form from int32 arrays (final gather of a result the row kernel wrote wide).
+__global__ void narrow_device_kernel(const int *indices, const int *data, size_t n, unsigned short *idx16, signed char *dat8)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        idx16[i] = (unsigned short)indices[i];
+        dat8[i] = (signed char)data[i];
+    }
+}
+
 // All conductors' data / indices, packed back to back (conductor-major) for a single read-back.
 // grid.y = conductor; src offsets are the per-conductor regions, dst offsets the running totals.
 __global__ void pack_all_kernel(const int *data, const int *indices, const unsigned short *idx16, const signed char *dat8,
@@ -729,40 +740,70 @@ __global__ void eigen_dot_kernel(const u32 *W, u32 P1, int K, int N, const int *
 }
 
 // ---------------------------------------------------------------------------
-// Integer-pipe microbenchmark: the roofline denominator.  Dependent chains of
-// IMAD (fma pipe) and IADD3/LOP3 (alu pipe), 8 independent chains per thread.
+// Integer-pipe microbenchmark: the roofline denominator.  Every step below is ONE PTX
+// instruction in an asm volatile statement, which ptxas turns into exactly one SASS
+// instruction (tests/test_cabi.py disassembles the library and checks it), so the operation
+// count of a launch is the number of statements executed, not an estimate from the source.
+//   KIND 0  IMAD only                      (fma pipe: 16 lanes/clk/SMSP)
+//   KIND 1  LOP3 only                      (alu pipe: 16 lanes/clk/SMSP)
+//   KIND 2  ADD only: ptxas itself splits these between IADD3 (alu) and IMAD.IADD (fma)
+//   KIND 3  IMAD and ADD alternating
+//   KIND 4  IMAD and LOP3 alternating
+// KIND 2-4 use both pipes and are bounded by the issue slot (1 warp instruction/clk/SMSP =
+// 148 x 4 x 32 x 1.965 GHz = 37.2 T int32-op/s nominal).  16 independent chains per thread.
 // ---------------------------------------------------------------------------
+#define TB_PEAK_IMAD(y) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(y) : "r"(m), "r"(c))
+#define TB_PEAK_ADD(x, z) asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(z))
+#define TB_PEAK_LOP(x, z) asm volatile("lop3.b32 %0, %0, %1, %2, 0x78;" : "+r"(x) : "r"(z), "r"(m))
+#define TB_PEAK_UNROLL 16          /* steps per loop iteration */
+#define TB_PEAK_OPS_SINGLE 8       /* instructions per step, KIND 0-2 */
+#define TB_PEAK_OPS_MIXED 16       /* instructions per step, KIND 3-4 */
+
 template <int KIND>
 __global__ void __launch_bounds__(256) int_peak_kernel(u32 *sink, int iters, u32 seed)
 {
-    // KIND 0: IMAD only (fma pipe); KIND 1: LOP3 only (alu pipe);
-    // KIND 2: one IMAD + one IADD3 per chain step (both pipes, issue-limited)
     u32 x0 = seed + threadIdx.x, x1 = x0 * 3u + 1u, x2 = x0 * 5u + 2u, x3 = x0 * 7u + 3u;
     u32 x4 = x0 * 11u + 4u, x5 = x0 * 13u + 5u, x6 = x0 * 17u + 6u, x7 = x0 * 19u + 7u;
+    u32 y0 = x0 ^ 1u, y1 = x1 ^ 2u, y2 = x2 ^ 3u, y3 = x3 ^ 4u, y4 = x4 ^ 5u, y5 = x5 ^ 6u, y6 = x6 ^ 7u, y7 = x7 ^ 8u;
     const u32 m = seed | 1u, c = seed ^ 0x9e3779b9u;
+#pragma unroll 1
     for (int i = 0; i < iters; ++i)
     {
 #pragma unroll
-        for (int u = 0; u < 16; ++u)
+        for (int u = 0; u < TB_PEAK_UNROLL; ++u)
         {
-            if (KIND == 0 || KIND == 2)
+            if (KIND == 0)
             {
-                x0 = x0 * m + c; x1 = x1 * m + c; x2 = x2 * m + c; x3 = x3 * m + c;
-                x4 = x4 * m + c; x5 = x5 * m + c; x6 = x6 * m + c; x7 = x7 * m + c;
+                TB_PEAK_IMAD(y0); TB_PEAK_IMAD(y1); TB_PEAK_IMAD(y2); TB_PEAK_IMAD(y3);
+                TB_PEAK_IMAD(y4); TB_PEAK_IMAD(y5); TB_PEAK_IMAD(y6); TB_PEAK_IMAD(y7);
             }
             if (KIND == 1)
             {
-                x0 ^= x1 & m; x1 ^= x2 & c; x2 ^= x3 & m; x3 ^= x4 & c;
-                x4 ^= x5 & m; x5 ^= x6 & c; x6 ^= x7 & m; x7 ^= x0 & c;
+                TB_PEAK_LOP(x0, x1); TB_PEAK_LOP(x1, x2); TB_PEAK_LOP(x2, x3); TB_PEAK_LOP(x3, x4);
+                TB_PEAK_LOP(x4, x5); TB_PEAK_LOP(x5, x6); TB_PEAK_LOP(x6, x7); TB_PEAK_LOP(x7, x0);
             }
             if (KIND == 2)
             {
-                x0 += x1 + m; x1 += x2 + m; x2 += x3 + m; x3 += x4 + m;
-                x4 += x5 + m; x5 += x6 + m; x6 += x7 + m; x7 += x0 + m;
+                TB_PEAK_ADD(x0, x1); TB_PEAK_ADD(x1, x2); TB_PEAK_ADD(x2, x3); TB_PEAK_ADD(x3, x4);
+                TB_PEAK_ADD(x4, x5); TB_PEAK_ADD(x5, x6); TB_PEAK_ADD(x6, x7); TB_PEAK_ADD(x7, x0);
+            }
+            if (KIND == 3)
+            {
+                TB_PEAK_IMAD(y0); TB_PEAK_ADD(x0, x1); TB_PEAK_IMAD(y1); TB_PEAK_ADD(x1, x2);
+                TB_PEAK_IMAD(y2); TB_PEAK_ADD(x2, x3); TB_PEAK_IMAD(y3); TB_PEAK_ADD(x3, x4);
+                TB_PEAK_IMAD(y4); TB_PEAK_ADD(x4, x5); TB_PEAK_IMAD(y5); TB_PEAK_ADD(x5, x6);
+                TB_PEAK_IMAD(y6); TB_PEAK_ADD(x6, x7); TB_PEAK_IMAD(y7); TB_PEAK_ADD(x7, x0);
+            }
+            if (KIND == 4)
+            {
+                TB_PEAK_IMAD(y0); TB_PEAK_LOP(x0, x1); TB_PEAK_IMAD(y1); TB_PEAK_LOP(x1, x2);
+                TB_PEAK_IMAD(y2); TB_PEAK_LOP(x2, x3); TB_PEAK_IMAD(y3); TB_PEAK_LOP(x3, x4);
+                TB_PEAK_IMAD(y4); TB_PEAK_LOP(x4, x5); TB_PEAK_IMAD(y5); TB_PEAK_LOP(x5, x6);
+                TB_PEAK_IMAD(y6); TB_PEAK_LOP(x6, x7); TB_PEAK_IMAD(y7); TB_PEAK_LOP(x7, x0);
             }
         }
     }
-    u32 r = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+    u32 r = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7 ^ y0 ^ y1 ^ y2 ^ y3 ^ y4 ^ y5 ^ y6 ^ y7;
     if (r == 0x12345678u) sink[0] = r;
 }
 

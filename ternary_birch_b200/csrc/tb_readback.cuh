@@ -160,6 +160,7 @@ static size_t narrow_chunk_entries()
 }
 #define TB_NARROW_CHUNK (narrow_chunk_entries())
 
+#if defined(__x86_64__)
 __attribute__((target("avx2"))) static void widen_u16_avx2(const unsigned short *src, int32_t *dst, size_t n)
 {
     size_t i = 0;
@@ -203,18 +204,23 @@ static int widen_isa()
                            : __builtin_cpu_supports("avx2") ? 1 : 0;
     return isa;
 }
+#else
+static int widen_isa() { return 0; }      // other hosts (aarch64 Grace): the scalar loops below, auto-vectorised
+#endif
 static void widen_u16(const unsigned short *src, int32_t *dst, size_t n)
 {
+#if defined(__x86_64__)
     if (widen_isa() == 2) { widen_u16_avx512(src, dst, n); return; }
-    static const bool avx2 = __builtin_cpu_supports("avx2");
-    if (avx2) { widen_u16_avx2(src, dst, n); return; }
+    if (widen_isa() == 1) { widen_u16_avx2(src, dst, n); return; }
+#endif
     for (size_t i = 0; i < n; ++i) dst[i] = src[i];
 }
 static void widen_i8(const signed char *src, int32_t *dst, size_t n)
 {
+#if defined(__x86_64__)
     if (widen_isa() == 2) { widen_i8_avx512(src, dst, n); return; }
-    static const bool avx2 = __builtin_cpu_supports("avx2");
-    if (avx2) { widen_i8_avx2(src, dst, n); return; }
+    if (widen_isa() == 1) { widen_i8_avx2(src, dst, n); return; }
+#endif
     for (size_t i = 0; i < n; ++i) dst[i] = src[i];
 }
 
@@ -267,7 +273,6 @@ struct Copier {
     std::condition_variable cv;
     std::deque<CopyRequest> q;
     bool stop = false;
-    std::string error;
     cudaStream_t stream = nullptr;
     char *stage[SLOTS] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev[SLOTS] = {nullptr, nullptr, nullptr};
@@ -277,25 +282,39 @@ struct Copier {
     void body()
     {
         cudaSetDevice(device);
+        ReadbackPolicy &policy = readback_policy();
         std::deque<Chunk> flight;
         CopyRequest cur;
         size_t cur_off = 0;
         bool have = false;
         uint64_t issued = 0;
+        // one busy period = from the first DMA issued on an idle copier to the last chunk widened
+        std::chrono::steady_clock::time_point busy_t0;
+        double busy_bytes = 0;
+        bool busy = false;
         for (;;)
         {
+            if (!busy && flight.empty()) { busy_t0 = std::chrono::steady_clock::now(); busy_bytes = 0; }
             while (flight.size() < 2 && fill_one(flight, cur, cur_off, have, issued)) {}
             if (flight.empty())
             {
+                if (busy)
+                {
+                    policy.record(ReadbackPolicy::NARROW, busy_bytes,
+                                  std::chrono::duration<double>(std::chrono::steady_clock::now() - busy_t0).count());
+                    busy = false;
+                }
                 std::unique_lock<std::mutex> lk(mx);
                 cv.wait(lk, [&] { return stop || !q.empty(); });
                 if (stop && q.empty()) return;
                 continue;
             }
+            busy = true;
             const Chunk c = flight.front();
             flight.pop_front();
             const cudaError_t e = cudaEventSynchronize(ev[c.slot]);
-            if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(mx); error = cudaGetErrorString(e); }
+            if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(c.req.h->copy_mx); c.req.h->copy_error = cudaGetErrorString(e); }
+            busy_bytes += (double)c.len * 4.0 * ((c.req.indices ? 1 : 0) + (c.req.data ? 1 : 0));
             // issue the next DMA before widening this chunk: its slot (issue order modulo 3) is neither
             // this chunk's nor the one still in flight, and its previous user was widened an iteration ago
             fill_one(flight, cur, cur_off, have, issued);
@@ -335,7 +354,7 @@ struct Copier {
         if (cur.indices) e = cudaMemcpyAsync(s_idx, cur.d_idx + c.off, c.len * 2, cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess && cur.data) e = cudaMemcpyAsync(s_dat, cur.d_dat + c.off, c.len, cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess) e = cudaEventRecord(ev[c.slot], stream);
-        if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(mx); error = cudaGetErrorString(e); }
+        if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(cur.h->copy_mx); cur.h->copy_error = cudaGetErrorString(e); }
         flight.push_back(c);
         return true;
     }
@@ -386,42 +405,11 @@ static int ensure_wide(tb_hecke *h, int64_t k)
     return TB_OK;
 }
 
-// The narrow read-back only pays where the host can widen faster than PCIe delivers plain int32
-// (~55 GB/s): measured once per process on 16 M entries with the pool (a few tens of ms).
-static bool host_widens_fast_enough()
-{
-    static const bool ok = [] {
-        if (getenv("TBIRCH_FORCE_NARROW_COPY")) return true;
-        const size_t n = (size_t)16 << 20;
-        unsigned short *idx = (unsigned short *)aligned_alloc(64, n * 2);
-        signed char *dat = (signed char *)aligned_alloc(64, n);
-        int32_t *oi = (int32_t *)aligned_alloc(64, n * 4), *od = (int32_t *)aligned_alloc(64, n * 4);
-        bool fast = false;
-        if (idx && dat && oi && od)
-        {
-            memset(idx, 1, n * 2); memset(dat, 1, n); memset(oi, 0, n * 4); memset(od, 0, n * 4);   // fault the pages in first
-            double best = 0;
-            for (int rep = 0; rep < 3; ++rep)
-            {
-                const WidenJob job{idx, dat, oi, od, n};
-                const auto t0 = std::chrono::steady_clock::now();
-                widen_run(job);
-                const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-                best = std::max(best, (double)n * 8.0 / sec / 1e9);
-            }
-            fast = best >= 70.0;
-        }
-        free(idx); free(dat); free(oi); free(od);
-        return fast;
-    }();
-    return ok;
-}
-
 static bool narrow_applies(const tb_hecke *h, int64_t k, const int32_t *data, const int32_t *indices)
 {
+    // (whether the row kernel wrote the narrow form at all was ReadbackPolicy's call at compute time)
     return h->d_idx16.ptr && h->maxmult <= 127 && h->nnz[k] >= h->g->narrow_min_nnz &&
-           (data || indices) && host_pointer(data) && host_pointer(indices) &&
-           (h->g->narrow_min_nnz < (1 << 18) || host_widens_fast_enough());
+           (data || indices) && host_pointer(data) && host_pointer(indices);
 }
 
 // data / indices of conductor k -> host arrays through the 3-byte format.  Returns at once;
@@ -467,16 +455,21 @@ extern "C" int tb_hecke_copy_wait(tb_hecke *h)
     {
         TB_CUDA(cudaEventSynchronize(h->copy_ev));
         h->copy_ev_armed = false;
-    }
-    if (h->g->copier)
-    {
-        std::lock_guard<std::mutex> lk(h->g->copier->mx);
-        if (!h->g->copier->error.empty())
+        if (h->plain_bytes > 0)
         {
-            const std::string msg = "libtbirch: read-back failed: " + h->g->copier->error;
-            h->g->copier->error.clear();
-            return fail(TB_ERR_RUNTIME, msg);
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, h->plain_ev0, h->plain_ev1) == cudaSuccess)
+                readback_policy().record(ReadbackPolicy::PLAIN, h->plain_bytes, ms * 1e-3);
+            cudaGetLastError();
+            h->plain_bytes = 0;
         }
+    }
+    std::lock_guard<std::mutex> lk(h->copy_mx);
+    if (!h->copy_error.empty())
+    {
+        const std::string msg = "libtbirch: read-back failed: " + h->copy_error;
+        h->copy_error.clear();
+        return fail(TB_ERR_RUNTIME, msg);
     }
     return TB_OK;
 }
@@ -494,8 +487,21 @@ extern "C" int tb_hecke_copy_sparse_async(tb_hecke *h, int64_t k, int32_t *data,
     else
     {
         if (int rc = ensure_wide(h, k)) return rc;
+        // large copies into host memory are timed for ReadbackPolicy: first copy of this T_p .. last one
+        const bool timed = (int64_t)nnz >= h->g->narrow_min_nnz && (data || indices) && host_pointer(data) && host_pointer(indices);
+        if (timed && !h->plain_ev0)
+        {
+            TB_CUDA(cudaEventCreate(&h->plain_ev0));
+            TB_CUDA(cudaEventCreate(&h->plain_ev1));
+        }
+        if (timed && h->plain_bytes == 0) TB_CUDA(cudaEventRecord(h->plain_ev0, st));
         if (nnz && data) TB_CUDA(cudaMemcpyAsync(data, h->d_data.ptr + h->nnzbase[k], nnz * sizeof(int), cudaMemcpyDefault, st));
         if (nnz && indices) TB_CUDA(cudaMemcpyAsync(indices, h->d_indices.ptr + h->nnzbase[k], nnz * sizeof(int), cudaMemcpyDefault, st));
+        if (timed)
+        {
+            TB_CUDA(cudaEventRecord(h->plain_ev1, st));
+            h->plain_bytes += (double)nnz * 4.0 * ((data ? 1 : 0) + (indices ? 1 : 0));
+        }
     }
     if (indptr) TB_CUDA(cudaMemcpyAsync(indptr, h->d_indptr.ptr + h->rowbase[k], ((size_t)h->rows[k] + 1) * sizeof(int), cudaMemcpyDefault, st));
     if (!h->copy_ev) TB_CUDA(cudaEventCreateWithFlags(&h->copy_ev, cudaEventDisableTiming));
@@ -516,8 +522,16 @@ extern "C" int tb_hecke_copy_sparse(tb_hecke *h, int64_t k, int32_t *data, int32
     else
     {
         if (int rc = ensure_wide(h, k)) return rc;
+        const bool timed = (int64_t)nnz >= h->g->narrow_min_nnz && (data || indices) && host_pointer(data) && host_pointer(indices);
+        const auto t0 = std::chrono::steady_clock::now();
         if (nnz && data) if (int rc = copy_out(h->g, data, h->d_data.ptr + h->nnzbase[k], nnz * sizeof(int))) return rc;
         if (nnz && indices) if (int rc = copy_out(h->g, indices, h->d_indices.ptr + h->nnzbase[k], nnz * sizeof(int))) return rc;
+        if (timed)
+        {
+            TB_CUDA(cudaStreamSynchronize(st));
+            readback_policy().record(ReadbackPolicy::PLAIN, (double)nnz * 4.0 * ((data ? 1 : 0) + (indices ? 1 : 0)),
+                                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        }
     }
     if (indptr) if (int rc = copy_out(h->g, indptr, h->d_indptr.ptr + h->rowbase[k], ((size_t)h->rows[k] + 1) * sizeof(int))) return rc;
     TB_CUDA(cudaStreamSynchronize(st));
@@ -531,6 +545,8 @@ extern "C" int tb_hecke_copy_sparse(tb_hecke *h, int64_t k, int32_t *data, int32
 extern "C" int tb_hecke_copy_sparse_all(tb_hecke *h, int32_t *data_all, int32_t *indices_all, int32_t *indptr_all)
 {
     if (!h) return fail(TB_ERR_INVALID_ARGUMENT, "tb_hecke_copy_sparse_all: null argument");
+    if ((data_all == nullptr) != (indices_all == nullptr))
+        return fail(TB_ERR_INVALID_ARGUMENT, "tb_hecke_copy_sparse_all: pass both data_all and indices_all, or neither");
     tb_genus *g = h->g;
     cudaStream_t st = g->stream;
     const int C = h->C;
@@ -622,8 +638,127 @@ extern "C" int tb_host_widen_probe(int64_t entries, double *out_gbps, int *threa
 extern "C" int64_t tb_hecke_transfer_bytes(const tb_hecke *h, int64_t k)
 {
     if (!h || k < 0 || k >= h->C) return 0;
-    const bool narrow = h->d_idx16.ptr && h->maxmult <= 127 && h->nnz[k] >= h->g->narrow_min_nnz &&
-                        (h->g->narrow_min_nnz < (1 << 18) || host_widens_fast_enough());
+    const bool narrow = h->d_idx16.ptr && h->maxmult <= 127 && h->nnz[k] >= h->g->narrow_min_nnz;
     return h->nnz[k] * (narrow ? 3 : 8) + ((int64_t)h->rows[k] + 1) * 4;
+}
+
+/* ReadbackPolicy's current view on this device (diagnostic for bench.py): running delivered GB/s of
+ * int32 CSR per format, how many large read-backs fed each, and the format in use (0 plain, 1 narrow). */
+extern "C" int tb_readback_stats(double *plain_gbps, double *narrow_gbps, int *plain_samples, int *narrow_samples, int *current)
+{
+    ReadbackPolicy &pol = readback_policy();
+    std::lock_guard<std::mutex> lk(pol.mx);
+    if (plain_gbps) *plain_gbps = pol.rate[0];
+    if (narrow_gbps) *narrow_gbps = pol.rate[1];
+    if (plain_samples) *plain_samples = pol.samples[0];
+    if (narrow_samples) *narrow_samples = pol.samples[1];
+    if (current) *current = pol.current;
+    return TB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Final integer gather of the Hecke rows: the one exchange of the multi-GPU path.
+// Each rank packs ALL conductors of its tb_hecke into one contiguous device buffer in the
+// 3-byte form (uint16 column, int8 entry; int32 pairs when a column or an entry does not fit),
+// the caller moves the buffers rank -> root with grouped send/recv over NVLink
+// (ternary_birch_b200/shard.py: torch.distributed is the transport, nothing is padded), and the
+// root widens each buffer into the reference's int32 CSR with tb_unpack_rows.
+// Layout per conductor k, each section padded to 16 bytes:
+//     columns[nnz_k] | entries[nnz_k] | indptr[rows_k + 1] (int32)
+// ---------------------------------------------------------------------------
+static size_t pad16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+static bool pack_narrow_ok(const tb_hecke *h)
+{
+    int64_t max_dim = 0;
+    for (int k = 0; k < h->C; ++k) max_dim = std::max<int64_t>(max_dim, h->g->dims[k]);
+    return max_dim <= 65536 && h->maxmult <= 127;
+}
+
+/* Bytes tb_hecke_pack writes for `h`, and through *entry_bytes the form: 3 (uint16 + int8) or 8 (int32 + int32). */
+extern "C" int64_t tb_hecke_packed_bytes(const tb_hecke *h, int *entry_bytes)
+{
+    if (!h) return 0;
+    const bool narrow = pack_narrow_ok(h);
+    if (entry_bytes) *entry_bytes = narrow ? 3 : 8;
+    size_t total = 0;
+    for (int k = 0; k < h->C; ++k)
+    {
+        const size_t n = (size_t)h->nnz[k];
+        total += pad16(n * (narrow ? 2 : 4)) + pad16(n * (narrow ? 1 : 4)) + pad16(((size_t)h->rows[k] + 1) * 4);
+    }
+    return (int64_t)total;
+}
+
+extern "C" int tb_hecke_pack(tb_hecke *h, void *dst_device, void *cuda_stream)
+{
+    if (!h || !dst_device) return fail(TB_ERR_INVALID_ARGUMENT, "tb_hecke_pack: null argument");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const bool narrow = pack_narrow_ok(h);
+    const bool have_narrow = h->d_idx16.ptr != nullptr;
+    char *out = (char *)dst_device;
+    for (int k = 0; k < h->C; ++k)
+    {
+        const size_t n = (size_t)h->nnz[k];
+        char *cols = out, *vals = cols + pad16(n * (narrow ? 2 : 4)), *ptr = vals + pad16(n * (narrow ? 1 : 4));
+        if (n && narrow && have_narrow)
+        {
+            TB_CUDA(cudaMemcpyAsync(cols, h->d_idx16.ptr + h->nnzbase[k], n * 2, cudaMemcpyDeviceToDevice, st));
+            TB_CUDA(cudaMemcpyAsync(vals, h->d_dat8.ptr + h->nnzbase[k], n, cudaMemcpyDeviceToDevice, st));
+        }
+        else if (n && narrow)
+        {
+            const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+            narrow_device_kernel<<<blocks, 256, 0, st>>>(h->d_indices.ptr + h->nnzbase[k], h->d_data.ptr + h->nnzbase[k], n,
+                                                        (unsigned short *)cols, (signed char *)vals);
+            ++g_launches;
+            TB_CUDA(cudaGetLastError());
+        }
+        else if (n)
+        {
+            if (int rc = ensure_wide(h, k)) return rc;
+            TB_CUDA(cudaMemcpyAsync(cols, h->d_indices.ptr + h->nnzbase[k], n * 4, cudaMemcpyDeviceToDevice, st));
+            TB_CUDA(cudaMemcpyAsync(vals, h->d_data.ptr + h->nnzbase[k], n * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        TB_CUDA(cudaMemcpyAsync(ptr, h->d_indptr.ptr + h->rowbase[k], ((size_t)h->rows[k] + 1) * 4, cudaMemcpyDeviceToDevice, st));
+        out = ptr + pad16(((size_t)h->rows[k] + 1) * 4);
+    }
+    return TB_OK;
+}
+
+/* Root side: one rank's packed buffer (device) -> int32 CSR (device), conductors back to back:
+ * data_all / indices_all hold sum nnz[k] entries, indptr_all sum (rows[k] + 1). */
+extern "C" int tb_unpack_rows(const void *packed_device, int entry_bytes, int64_t C, const int64_t *nnz, const int64_t *rows,
+                              int32_t *data_all, int32_t *indices_all, int32_t *indptr_all, void *cuda_stream)
+{
+    if (!packed_device || !nnz || !rows || (entry_bytes != 3 && entry_bytes != 8))
+        return fail(TB_ERR_INVALID_ARGUMENT, "tb_unpack_rows: bad argument");
+    if (int rc = require_device()) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const bool narrow = entry_bytes == 3;
+    const char *in = (const char *)packed_device;
+    size_t e = 0, r = 0;
+    for (int64_t k = 0; k < C; ++k)
+    {
+        const size_t n = (size_t)nnz[k], np1 = (size_t)rows[k] + 1;
+        const char *cols = in, *vals = cols + pad16(n * (narrow ? 2 : 4)), *ptr = vals + pad16(n * (narrow ? 1 : 4));
+        if (n && narrow)
+        {
+            const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+            widen_device_kernel<<<blocks, 256, 0, st>>>((const unsigned short *)cols, (const signed char *)vals, n,
+                                                       indices_all + e, data_all + e);
+            ++g_launches;
+            TB_CUDA(cudaGetLastError());
+        }
+        else if (n)
+        {
+            TB_CUDA(cudaMemcpyAsync(indices_all + e, cols, n * 4, cudaMemcpyDeviceToDevice, st));
+            TB_CUDA(cudaMemcpyAsync(data_all + e, vals, n * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        TB_CUDA(cudaMemcpyAsync(indptr_all + r, ptr, np1 * 4, cudaMemcpyDeviceToDevice, st));
+        e += n; r += np1;
+        in = ptr + pad16(np1 * 4);
+    }
+    return TB_OK;
 }
 

@@ -30,7 +30,9 @@
 #include <condition_variable>
 #include <mutex>
 #include <thread>
+#if defined(__x86_64__)
 #include <immintrin.h>
+#endif
 #include <sys/resource.h>
 #include <sys/syscall.h>
 #include <unistd.h>
@@ -175,10 +177,16 @@ static void base_point(HostFp &F, const int64_t *q, uint32_t out[3])
 // ---------------------------------------------------------------------------
 // device buffer helper
 // ---------------------------------------------------------------------------
+// (both helpers release in their destructor, so every early error return of an entry point
+//  gives its device memory back; explicit release() calls remain where the order matters)
 template <class T>
 struct DevBuf {
     T *ptr = nullptr;
     size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
     cudaError_t reserve(size_t n)
     {
         if (n <= cap) return cudaSuccess;
@@ -205,6 +213,10 @@ struct PoolBuf {
     T *ptr = nullptr;
     size_t cap = 0;
     cudaStream_t stream = 0;
+    PoolBuf() = default;
+    PoolBuf(const PoolBuf &) = delete;
+    PoolBuf &operator=(const PoolBuf &) = delete;
+    ~PoolBuf() { release(); }
     cudaError_t reserve(size_t n, cudaStream_t st)
     {
         if (n <= cap) return cudaSuccess;
@@ -233,6 +245,53 @@ struct PrimeState {
 
 struct Copier;
 static void copier_destroy(Copier *c);
+
+// ---------------------------------------------------------------------------
+// Which read-back format delivers a large T_p to host memory faster ON THIS RANK: the plain
+// int32 DMA (8 bytes per entry over PCIe, no host work) or the 3-byte device format widened by
+// host threads (tb_readback.cuh)?  It depends on the host, on how many ranks share it and on
+// which PCIe path this GPU sits behind (profiles/r2a_d2h_probe_n4.md: with four GPUs copying at
+// once two get 44 GB/s and two 21 GB/s, and host stores compete with the DMA for one memory
+// system), so it is measured, not assumed: every large host read-back reports the int32-CSR
+// bytes it delivered and the time it was busy, the policy keeps a running rate per format,
+// tries each format first and re-tries the losing one now and then.  One policy per device
+// (ranks are processes; a process driving several GPUs keeps them apart).
+// ---------------------------------------------------------------------------
+struct ReadbackPolicy {
+    enum { PLAIN = 0, NARROW = 1 };
+    std::mutex mx;
+    double rate[2] = {0.0, 0.0};      // running delivered GB/s of int32 CSR per format
+    int samples[2] = {0, 0};
+    int current = NARROW;
+    uint64_t decisions = 0;
+
+    int choose()
+    {
+        std::lock_guard<std::mutex> lk(mx);
+        ++decisions;
+        if (samples[NARROW] < 2) return NARROW;
+        if (samples[PLAIN] < 2) return PLAIN;
+        if (rate[1 - current] > 1.15 * rate[current]) current = 1 - current;   // hysteresis: ranks adapt concurrently
+        if (decisions % 24 == 0) return 1 - current;                           // the host's load changes: look again
+        return current;
+    }
+    void record(int format, double csr_bytes, double seconds)
+    {
+        if (csr_bytes < 64e6 || seconds <= 0) return;      // small copies measure latency, not the path
+        std::lock_guard<std::mutex> lk(mx);
+        const double r = csr_bytes / seconds / 1e9;
+        rate[format] = samples[format] ? 0.5 * rate[format] + 0.5 * r : r;
+        ++samples[format];
+    }
+};
+
+static ReadbackPolicy &readback_policy()
+{
+    static ReadbackPolicy per_device[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return per_device[dev & 63];
+}
 
 struct tb_genus {
     int N = 0, K = 0;
@@ -265,12 +324,14 @@ struct tb_genus {
     int *h_maxmult = nullptr;   // pinned [1]
     struct Copier *copier = nullptr;   // background thread of the narrow read-back (started on first use)
     bool allow_narrow = true;     // TBIRCH_NO_NARROW_COPY turns the compressed read-back off
+    bool force_narrow = false;    // TBIRCH_FORCE_NARROW_COPY: always the 3-byte format where it applies (no measuring)
     int64_t narrow_min_nnz = 1 << 18;   // smaller matrices are copied as they are (TBIRCH_NARROW_MIN_NNZ)
     int64_t narrow_max_ratio = 32;      // narrow row output is attempted while (p+1)/N stays below this (TBIRCH_NARROW_MAX_RATIO)
     bool allow_fused = true;
     bool force_checked = false;   // TBIRCH_FORCE_CHECKED: always run the checked C128 kernel in precise mode
     int last_int_mode = -1;       // tb_last_int_mode
     bool force_wide = false;      // TBIRCH_FORCE_WIDE: never run precise launches in the bounded 64-bit mode
+    bool no_fp64_reduce = false;  // TBIRCH_NO_FP64_REDUCE: every reduction through the integer loop (parity tests of the fallback)
     size_t device_bytes = 0;
     // per-shard row bookkeeping of the last Hecke call (reused while the shard is unchanged)
     int shard_begin = -1, shard_end = -1;
@@ -310,6 +371,16 @@ struct tb_hecke {
     int copy_pending = 0;
     cudaEvent_t copy_ev = nullptr;     // last plain cudaMemcpyAsync of an asynchronous copy
     bool copy_ev_armed = false;
+    // timing of the plain asynchronous host read-back of this T_p (ReadbackPolicy)
+    cudaEvent_t plain_ev0 = nullptr, plain_ev1 = nullptr;
+    double plain_bytes = 0;
+    std::string copy_error;            // failure of a background read-back of THIS result
+    ~tb_hecke()
+    {
+        if (copy_ev) cudaEventDestroy(copy_ev);
+        if (plain_ev0) cudaEventDestroy(plain_ev0);
+        if (plain_ev1) cudaEventDestroy(plain_ev1);
+    }
 };
 
 struct tb_isoseq {
@@ -481,10 +552,9 @@ extern "C" int tb_genus_create(const tb_genus_desc *d, tb_genus **out)
     g->allow_fused = getenv("TBIRCH_TWO_PASS_ROWS") == nullptr;   // debugging / A-B switches
     g->force_checked = getenv("TBIRCH_FORCE_CHECKED") != nullptr;
     g->force_wide = getenv("TBIRCH_FORCE_WIDE") != nullptr;
-    g->allow_narrow = getenv("TBIRCH_NO_NARROW_COPY") == nullptr;
-    // several ranks sharing one host saturate its memory system with widening traffic sooner than with
-    // plain DMA: keep the narrow read-back for one or two processes per host
-    if (const char *e = getenv("LOCAL_WORLD_SIZE")) if (atoi(e) > 2 && !getenv("TBIRCH_FORCE_NARROW_COPY")) g->allow_narrow = false;
+    g->no_fp64_reduce = getenv("TBIRCH_NO_FP64_REDUCE") != nullptr;
+    g->allow_narrow = getenv("TBIRCH_NO_NARROW_COPY") == nullptr;   // otherwise ReadbackPolicy decides per T_p,
+    g->force_narrow = getenv("TBIRCH_FORCE_NARROW_COPY") != nullptr; // unless this pins the 3-byte format
     if (const char *e = getenv("TBIRCH_NARROW_MIN_NNZ")) g->narrow_min_nnz = std::max(1ll, atoll(e));
     if (const char *e = getenv("TBIRCH_NARROW_MAX_RATIO")) g->narrow_max_ratio = std::max(1ll, atoll(e));
     TB_CUDA(g->d_err.reserve(2));
@@ -601,6 +671,7 @@ static int setup_prime(tb_genus *g, uint64_t p)
     // FP64 reduce loop: isometry entries are bounded by p * sqrt(M / lambda_min) with M < 2^50 the
     // loop's entry guard on the coefficients (tb_neighbor.cuh); require that bound below 2^52.
     pc.fp64_reduce = ((double)p * sqrt(1125899906842624.0 / g->lambda_min) < 4503599627370496.0) ? 1u : 0u;
+    if (g->no_fp64_reduce) pc.fp64_reduce = 0u;       // TBIRCH_NO_FP64_REDUCE: the literal integer loop (eisenstein_reduce)
     if (pc.use_lut)
     {
         TB_CUDA(g->d_invlut.reserve(p));
@@ -871,7 +942,8 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     int64_t max_dim = 0;
     for (int k = 0; k < C; ++k) max_dim = std::max<int64_t>(max_dim, g->dims[k]);
     const bool narrow_possible = g->allow_narrow && max_dim <= 65536 && cap_total >= g->narrow_min_nnz &&
-                                 (P1 <= 127 || (int64_t)P1 <= g->narrow_max_ratio * (int64_t)N);
+                                 (P1 <= 127 || (int64_t)P1 <= g->narrow_max_ratio * (int64_t)N) &&
+                                 (g->force_narrow || readback_policy().choose() == ReadbackPolicy::NARROW);
 
     RowLaunch R;
     memset(&R, 0, sizeof(R));
@@ -1075,7 +1147,6 @@ extern "C" void tb_hecke_destroy(tb_hecke *h)
 {
     if (!h) return;
     tb_hecke_copy_wait(h);                       // an asynchronous read-back may still be reading the device arrays
-    if (h->copy_ev) cudaEventDestroy(h->copy_ev);
     h->d_indptr.release(); h->d_data.release(); h->d_indices.release(); h->d_idx16.release(); h->d_dat8.release();
     delete h;
 }
@@ -1537,18 +1608,27 @@ static int peak_one(double ops_per_iter_per_thread, double *out)
     return TB_OK;
 }
 
+extern "C" int tb_int_peak_detail(double out[5])
+{
+    if (!out) return fail(TB_ERR_INVALID_ARGUMENT, "tb_int_peak_detail: null argument");
+    if (int rc = require_device()) return rc;
+    // operations per inner iteration per thread = SASS instructions of the unrolled body (tb_kernels.cuh)
+    const double single = (double)TB_PEAK_UNROLL * TB_PEAK_OPS_SINGLE, mixed = (double)TB_PEAK_UNROLL * TB_PEAK_OPS_MIXED;
+    if (int rc = peak_one<0>(single, &out[0])) return rc;
+    if (int rc = peak_one<1>(single, &out[1])) return rc;
+    if (int rc = peak_one<2>(single, &out[2])) return rc;
+    if (int rc = peak_one<3>(mixed, &out[3])) return rc;
+    if (int rc = peak_one<4>(mixed, &out[4])) return rc;
+    return TB_OK;
+}
+
 extern "C" int tb_int_peak(double *imad, double *iadd, double *mixed)
 {
-    if (int rc = require_device()) return rc;
-    double a = 0, b = 0, c = 0;
-    // per inner iteration: 16 unrolled steps x 8 chains; KIND 0: 1 IMAD each; KIND 1: 1 LOP3 each;
-    // KIND 2: 1 IMAD + 1 LOP3 each
-    if (int rc = peak_one<0>(16.0 * 8.0, &a)) return rc;
-    if (int rc = peak_one<1>(16.0 * 8.0, &b)) return rc;
-    if (int rc = peak_one<2>(16.0 * 8.0 * 2.0, &c)) return rc;
-    if (imad) *imad = a;
-    if (iadd) *iadd = b;
-    if (mixed) *mixed = c;
+    double v[5];
+    if (int rc = tb_int_peak_detail(v)) return rc;
+    if (imad) *imad = v[0];
+    if (iadd) *iadd = v[1];
+    if (mixed) *mixed = std::max(v[2], std::max(v[3], v[4]));
     return TB_OK;
 }
 

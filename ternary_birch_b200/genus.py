@@ -313,6 +313,16 @@ class HeckeResult:
         cabi.check(cabi.lib().tb_hecke_copy_sparse_async(self._h, k, ctypes.c_void_p(data_ptr), ctypes.c_void_p(indices_ptr),
                                                          ctypes.c_void_p(indptr_ptr), ctypes.c_void_p(cuda_stream)))
 
+    def packed_bytes(self):
+        """(bytes, entry_bytes) of the one-buffer form the final gather ships (tb_hecke_pack)."""
+        fmt = ctypes.c_int()
+        n = int(cabi.lib().tb_hecke_packed_bytes(self._h, ctypes.byref(fmt)))
+        return n, int(fmt.value)
+
+    def pack_to(self, device_ptr: int, cuda_stream: int) -> None:
+        """All conductors into one device buffer of packed_bytes()[0] bytes, enqueued on `cuda_stream`."""
+        cabi.check(cabi.lib().tb_hecke_pack(self._h, ctypes.c_void_p(device_ptr), ctypes.c_void_p(cuda_stream)))
+
     def sparse(self, k):
         rows, _, nnz = self.shape(k)
         data = np.empty(nnz, dtype=np.int32)

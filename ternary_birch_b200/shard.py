@@ -106,45 +106,108 @@ def gather_csr(local: dict, device=None, group=None, dst: int = 0):
     return out
 
 
-def gather_hecke_device(result, device, group=None, dst: int = 0):
-    """Final integer gather of device-resident Hecke rows (a `HeckeResult`) to rank `dst`.
+_P2P_WARM = set()
 
-    Each rank lays its CSR arrays out in ONE int32 device tensor (copied device-to-device out
-    of the library's buffers), the tensors are padded to the largest rank and gathered over
-    NCCL/NVLink.  Returns on dst: (headers, payloads) with headers[r] = int64 [C, then per
-    conductor: conductor, nnz, rows+1] and payloads[r] an int32 device tensor holding, per
-    conductor, data | indices | indptr; None elsewhere.
+
+def gather_hecke_device(result, device, group=None, dst: int = 0, widen: bool = True):
+    """Final integer gather of device-resident Hecke rows (a `HeckeResult`) to rank `dst` over NCCL.
+
+    Every rank packs all its conductors into ONE device buffer in the 3-byte form
+    (`tb_hecke_pack`: uint16 column + int8 entry, int32 pairs when they do not fit), the
+    sizes travel in one small all_gather, and the buffers go rank -> dst as grouped
+    send/recv (`batch_isend_irecv`: one NCCL group, nothing padded, one receive buffer of the
+    exact total).  On dst each rank's buffer is widened on the device into the reference's
+    int32 CSR (`tb_unpack_rows`).  The first call per process pair also pays NCCL's
+    point-to-point connection set-up; `warm_gather` does that outside a timed region.
+
+    Returns on dst a list over ranks of {conductor: (data, indices, indptr)} int32 device
+    tensors (views into one buffer per rank), plus the byte counts; None elsewhere.
     """
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    from . import cabi
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    stream = torch.cuda.current_stream(device)
+    C = result.num_conductors()
+    nbytes, fmt = result.packed_bytes()
+    meta = [nbytes, fmt]
+    for k in range(C):
+        rows, _, nnz = result.shape(k)
+        meta += [result.conductor(k), nnz, rows]
+    meta_t = torch.tensor(meta, dtype=torch.int64, device=device)
+    metas = [torch.zeros_like(meta_t) for _ in range(world)]
+    dist.all_gather(metas, meta_t, group=group)
+    metas = torch.stack(metas).cpu().numpy()
+    sizes = [int(m[0]) for m in metas]
+
+    packed = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
+    result.pack_to(packed.data_ptr(), stream.cuda_stream)
+    ops, recv, offs = [], None, None
+    if rank == dst:
+        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        recv = torch.empty(max(int(offs[-1]), 16), dtype=torch.uint8, device=device)
+        recv[int(offs[dst]):int(offs[dst]) + nbytes].copy_(packed[:nbytes])
+        for r in range(world):
+            if r != dst and sizes[r] > 0:
+                ops.append(dist.P2POp(dist.irecv, recv[int(offs[r]):int(offs[r + 1])], r, group))
+    elif nbytes > 0:
+        ops.append(dist.P2POp(dist.isend, packed[:nbytes], dst, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    if rank != dst:
+        return None
+    out = []
+    L = cabi.lib()
+    for r in range(world):
+        m = metas[r]
+        conds = [int(m[2 + 3 * k]) for k in range(C)]
+        nnz = np.ascontiguousarray([int(m[3 + 3 * k]) for k in range(C)], dtype=np.int64)
+        rows = np.ascontiguousarray([int(m[4 + 3 * k]) for k in range(C)], dtype=np.int64)
+        if not widen:
+            out.append(dict(conductors=conds, nnz=nnz, rows=rows, entry_bytes=int(m[1]),
+                            packed=recv[int(offs[r]):int(offs[r + 1])]))
+            continue
+        tot, totp = int(nnz.sum()), int((rows + 1).sum())
+        buf = torch.empty(2 * tot + totp, dtype=torch.int32, device=device)
+        base = buf.data_ptr()
+        cabi.check(L.tb_unpack_rows(ctypes.c_void_p(recv.data_ptr() + int(offs[r])), int(m[1]), C, nnz.ctypes.data,
+                                    rows.ctypes.data, ctypes.c_void_p(base), ctypes.c_void_p(base + 4 * tot),
+                                    ctypes.c_void_p(base + 8 * tot), ctypes.c_void_p(stream.cuda_stream)))
+        part, e, p_ = {}, 0, 0
+        for k in range(C):
+            n, np1 = int(nnz[k]), int(rows[k]) + 1
+            part[conds[k]] = (buf[e:e + n], buf[tot + e:tot + e + n], buf[2 * tot + p_:2 * tot + p_ + np1])
+            e += n
+            p_ += np1
+        out.append(part)
+    return out, dict(bytes_per_rank=sizes, entry_bytes=[int(m[1]) for m in metas])
+
+
+def warm_gather(device, group=None, dst: int = 0):
+    """Set up NCCL's point-to-point connections rank -> dst once (they are made lazily on first
+    use and cost far more than the gather itself), so that a later gather_hecke_device runs at
+    link speed."""
     import torch
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    C = result.num_conductors()
-    header = [C]
-    total = 0
-    for k in range(C):
-        rows, _, nnz = result.shape(k)
-        header += [result.conductor(k), nnz, rows + 1]
-        total += 2 * nnz + rows + 1
-    payload = torch.empty(max(total, 1), dtype=torch.int32, device=device)
-    pos = 0
-    base = payload.data_ptr()
-    for k in range(C):
-        rows, _, nnz = result.shape(k)
-        result.copy_sparse_to(k, base + 4 * pos, base + 4 * (pos + nnz), base + 4 * (pos + 2 * nnz))
-        pos += 2 * nnz + rows + 1
-    hdr = torch.tensor(header + [total], dtype=torch.int64, device=device)
-    hdrs = [torch.zeros_like(hdr) for _ in range(world)]
-    dist.all_gather(hdrs, hdr, group=group)
-    max_total = max(int(h[-1]) for h in hdrs)
-    if payload.numel() < max_total:
-        padded = torch.zeros(max_total, dtype=torch.int32, device=device)
-        padded[:payload.numel()] = payload
-        payload = padded
+    key = (id(group), dst)
+    if key in _P2P_WARM:
+        return
+    tiny = torch.zeros(4, dtype=torch.uint8, device=device)
+    ops = []
+    if rank == dst:
+        bufs = [torch.zeros_like(tiny) for _ in range(world)]
+        ops = [dist.P2POp(dist.irecv, bufs[r], r, group) for r in range(world) if r != dst]
     else:
-        payload = payload[:max_total] if max_total > 0 else payload[:1]
-    bufs = [torch.empty_like(payload) for _ in range(world)] if rank == dst else None
-    dist.gather(payload, bufs, dst=dst, group=group)
-    if rank != dst:
-        return None
-    return [h[:-1].cpu().numpy() for h in hdrs], [b[:int(h[-1])] for b, h in zip(bufs, hdrs)]
+        ops = [dist.P2POp(dist.isend, tiny, dst, group)]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    torch.cuda.synchronize(device)
+    _P2P_WARM.add(key)

@@ -11,9 +11,17 @@
 #include <fstream>
 #include <iostream>
 
+#ifdef TB_FACADE_GMPXX
+#include <gmpxx.h>      // -I oracle/shim: a plain mpz_class over libgmp.so (this image has no GMP headers)
+#endif
+
 #include "../../ternary_birch_b200/host/Genus.h"
 #include "../../ternary_birch_b200/host/IsometrySequence.h"
 
+#ifdef TB_FACADE_GMPXX
+// the binding's own instantiation: R = mpz_class through host/birch.h's IntegerTraits<mpz_class>
+typedef mpz_class Big;
+#else
 // A minimal "big integer" to instantiate the precise (GMP-replacing) mode without GMP headers.
 struct Big {
     long long v;
@@ -29,6 +37,7 @@ template<> struct IntegerTraits<Big, void> {
     static Big from_i64(int64_t x) { return Big(x); }
 };
 }
+#endif
 
 static std::vector<int64_t> read_stream(const char *path)
 {

@@ -186,9 +186,20 @@ def find_rational_eigenvectors(ref, small_primes=(2, 3, 19, 23)):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--slow", action="store_true", help="also regenerate the minutes-long samples (C5, error cases)")
+    ap.add_argument("--bench", action="store_true",
+                    help="only add the digest of the bench workload itself (level 1009091, T_9973, int64: ~1 min, 8 GB of scratch) "
+                         "to hecke_digests_slow.json")
     args = ap.parse_args()
     if not RefBinary.available():
         sys.exit("oracle/_ref/birch_ref missing: make -C oracle ref")
+    if args.bench:
+        ref = RefBinary(1009091, 1)
+        slow = json.load(open(OUT / "hecke_digests_slow.json")) if (OUT / "hecke_digests_slow.json").exists() else {}
+        slow["L1009091_p9973_z64"] = [digest(m) for m in ref.hecke(9973, False, True)]
+        with open(OUT / "hecke_digests_slow.json", "w") as f:
+            json.dump(slow, f)
+        print("bench workload digest written")
+        return
 
     small = {}
     digests = {}

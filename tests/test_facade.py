@@ -20,6 +20,26 @@ def facade_binary(tmp_path_factory):
     return out
 
 
+@pytest.fixture(scope="module")
+def facade_binary_gmpxx(tmp_path_factory):
+    """The same program with R = mpz_class, so host/birch.h's IntegerTraits<mpz_class> (the
+    instantiation the Cython binding uses for precise=True) is compiled and run.  The image has
+    libgmp.so.10 but no GMP headers: oracle/shim supplies the declarations (test infrastructure)."""
+    out = tmp_path_factory.mktemp("facade") / "facade_test_gmpxx"
+    lib = ROOT / "ternary_birch_b200" / "libtbirch.so"
+    gmp = "/usr/lib/x86_64-linux-gnu/libgmp.so.10"
+    if not Path(gmp).exists():
+        pytest.skip("no libgmp.so.10 on this machine")
+    cmd = ["g++", "-std=c++11", "-O1", "-Wall", "-Werror", "-DTB_FACADE_GMPXX", "-I", str(ROOT / "oracle" / "shim"),
+           "-o", str(out), str(ROOT / "tests" / "cpp" / "facade_test.cpp"), str(lib), gmp, f"-Wl,-rpath,{lib.parent}"]
+    subprocess.run(cmd, check=True, cwd=str(ROOT))
+    return out
+
+
+def test_facade_compiles_with_mpz_class(facade_binary_gmpxx):
+    assert facade_binary_gmpxx.exists()
+
+
 def test_facade_compiles_against_the_cabi(facade_binary):
     """Same class templates / method names the pyx declares (pyx:45-118) compile with -Wall -Werror."""
     assert facade_binary.exists()
@@ -28,7 +48,9 @@ def test_facade_compiles_against_the_cabi(facade_binary):
 
 
 @pytest.mark.gpu
-def test_facade_matches_python_path(facade_binary, tables, tmp_path):
+@pytest.mark.parametrize("which", ["stand_in", "mpz_class"])
+def test_facade_matches_python_path(request, which, tables, tmp_path):
+    facade_binary = request.getfixturevalue("facade_binary" if which == "stand_in" else "facade_binary_gmpxx")
     from ternary_birch_b200 import Genus, IsometrySequence
     t = tables("85085")
     stream = tmp_path / "g.tbg"

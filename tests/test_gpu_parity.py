@@ -255,8 +255,9 @@ def test_size_independent_properties_full_size(genus):
     assert (TA != TA.T.tocsr()).nnz == 0            # T A is symmetric
 
 
-def test_bench_workload_properties(genus):
-    """The bench workload itself (C4: N = 10316, T_9973, int64 and precise): conductor-1 rows sum
+def test_bench_workload_properties(genus, hecke_digests):
+    """The bench workload itself (C4: N = 10316, T_9973, int64 and precise): every CSR array of all 8
+    conductors hashes to the digest of the unmodified reference's output, conductor-1 rows sum
     to p + 1, T A is symmetric for A = diag(|Aut|), both integer modes agree entry for entry, and
     the row blocks of a 3-way representative shard concatenate to the full matrix."""
     from scipy.sparse import csr_matrix
@@ -264,6 +265,11 @@ def test_bench_workload_properties(genus):
     g = genus("1009091", False)
     N = g.table.N
     full = g.hecke_matrix_sparse(p)
+    # the unmodified reference's output for exactly this call (tests/golden/make_golden.py --bench)
+    key = "L1009091_p9973_z64"
+    if key in hecke_digests:
+        t = g.table
+        assert [csr_digest(c, d, *full[int(c)]) for c, d in zip(t.conductors, t.dims)] == hecke_digests[key]
     data, indices, indptr = full[1]
     assert (np.add.reduceat(data.astype(np.int64), indptr[:-1]) == p + 1).all()
     T = csr_matrix((data.astype(np.int64), indices, indptr), shape=(N, N))
@@ -338,9 +344,10 @@ def test_narrow_readback_matches_plain(tables, monkeypatch, name, p, want_narrow
     got = {}
     for narrow in (False, True):
         monkeypatch.delenv("TBIRCH_NO_NARROW_COPY", raising=False)
+        monkeypatch.delenv("TBIRCH_FORCE_NARROW_COPY", raising=False)
         monkeypatch.setenv("TBIRCH_NARROW_MIN_NNZ", "1")
-        if not narrow:
-            monkeypatch.setenv("TBIRCH_NO_NARROW_COPY", "1")
+        # pin the format: left alone, the library picks it per rank from measured delivery rates
+        monkeypatch.setenv("TBIRCH_FORCE_NARROW_COPY" if narrow else "TBIRCH_NO_NARROW_COPY", "1")
         g = Genus(t, precise=True)
         try:
             res = g.hecke_device(p)
@@ -386,8 +393,11 @@ def test_row_kernel_variants_agree(tables, port_oracle, monkeypatch, env):
     for k in ("TBIRCH_TWO_PASS_ROWS", "TBIRCH_NARROW_MIN_NNZ", "TBIRCH_NARROW_MAX_RATIO", "TBIRCH_NO_NARROW_COPY",
               "TBIRCH_ROWS_SCRATCH"):
         monkeypatch.delenv(k, raising=False)
+    monkeypatch.delenv("TBIRCH_FORCE_NARROW_COPY", raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
+    if "TBIRCH_NARROW_MIN_NNZ" in env:
+        monkeypatch.setenv("TBIRCH_FORCE_NARROW_COPY", "1")   # the narrow attempt itself is under test, not the policy
     t = tables("85085")
     g = Genus(t, precise=True)
     try:
@@ -424,3 +434,75 @@ def test_row_kernel_global_scratch_walks_rows(tables, port_oracle, monkeypatch, 
             assert_same_csr(g.hecke_matrix_sparse(p), port_oracle("1062347").hecke(p, False), (two_pass, p))
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("name,p", [("85085", 101), ("1062347", 101), ("85085", 997)])
+def test_integer_reduce_fallback(tables, port_oracle, monkeypatch, name, p):
+    """The reduction normally runs in the exact FP64 loop; the literal integer loop (eisenstein_reduce,
+    QuadForm.h:530-691 statement by statement) is what out-of-range launches fall back to.
+    TBIRCH_NO_FP64_REDUCE sends every neighbor through it: records (reduced form AND isometry),
+    Hecke matrices and the isometry stream must still equal the oracle's, in both integer modes."""
+    from ternary_birch_b200 import Genus, IsometrySequence
+    monkeypatch.setenv("TBIRCH_NO_FP64_REDUCE", "1")
+    t = tables(name)
+    oracle = port_oracle(name)
+    rows = min(t.N, 48)
+    for precise in (False, True):
+        g = Genus(t, precise=precise)
+        try:
+            assert np.array_equal(g.neighbor_records(p, 0, rows), oracle.neighbor_records(p, precise)[:rows]), precise
+            assert_same_csr(g.hecke_matrix_sparse(p), oracle.hecke(p, precise), (name, p, precise))
+            if t.N * (p + 1) <= 200000:
+                seq = IsometrySequence(g, p)
+                assert np.array_equal(seq.read(t.N * (p + 1)), oracle.isometry_sequence(p, precise))
+                seq.close()
+        finally:
+            g.close()
+
+
+def test_checked_128_bit_mode_raises_the_reference_overflow(tables):
+    """precise=True replaces GMP by overflow-checked 128-bit arithmetic.  At p = 2^31 - 1 the second
+    shear of build_neighbor forms a * s2^2 with |s2| up to p^2 = 2^62 (NeighborManager.h:325-329), past
+    127 bits for any representative with a >= 8: the checked mode must notice and raise the reference's
+    overflow_error text (NeighborManager.h:350-352) instead of returning wrapped values.  (GMP itself
+    would succeed: documented deviation)  Reached through eigenvalues(), the only
+    call that makes p + 1 = 2^31 neighbors of ONE representative."""
+    from ternary_birch_b200 import EigenvectorManager, Genus
+    t = tables("1062347")
+    n = int(np.argmax(t.q[:, 0]))
+    assert t.q[n, 0] >= 8 and t.lut[0][n] != -1
+    g = Genus(t, precise=True)
+    try:
+        vec = np.zeros(int(t.dims[0]), dtype=np.int32)
+        vec[int(t.lut[0][n])] = 1
+        man = EigenvectorManager()
+        man.add_eigenvector(g.eigenvector(vec, 1))
+        man.finalize()
+        with pytest.raises(OverflowError) as info:
+            g.eigenvalues(man, 2147483647)
+        assert str(info.value) == "An overflow has occurred. The p-neighbor's discriminant does not match the original."
+        assert g.last_int_mode() == "int128-checked"
+        # the same call at a prime the 128-bit pipeline does hold still works afterwards
+        assert len(g.eigenvalues(man, 65537)) == 1
+    finally:
+        g.close()
+
+
+def test_failing_calls_release_device_memory(tables):
+    """A call that ends in the reference's overflow / "Key not found." error must give back the device
+    buffers it reserved (GBs at large p): repeated failures leave the free-memory figure flat."""
+    import torch
+    from ternary_birch_b200 import Genus
+    g = Genus(tables("1062347"), precise=False)
+    try:
+        free = []
+        for _ in range(6):
+            with pytest.raises((OverflowError, ValueError)):
+                g.hecke_matrix_sparse(40009)
+            torch.cuda.synchronize()
+            free.append(torch.cuda.mem_get_info()[0])
+        # the stream-ordered pool keeps what it once allocated; it must not keep growing
+        assert free[-1] >= free[1] - (64 << 20), free
+    finally:
+        g.close()
+
