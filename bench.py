@@ -366,9 +366,10 @@ def main():
         ev.record(copy_stream)
         pending[slot] = (res, ev)
 
-    # warm-up: W untimed steps, at least six: both pinned result sets must have been written by the host
-    # once (the first CPU store to a page of a fresh cudaHostAlloc mapping takes a minor fault)
-    for i in range(max(6, args.warmup)):
+    # warm-up: W untimed steps, at least eight: both pinned result sets must have been written by the host
+    # once (the first CPU store to a page of a fresh cudaHostAlloc mapping takes a minor fault), and the library
+    # measures one read-back in each format before it settles on one (tb_readback_stats)
+    for i in range(max(8, args.warmup)):
         step_e2e(i)
     drain(0)
     drain(1)
@@ -458,9 +459,10 @@ def main():
     # ---- roofline of the dominant kernel (neighbors_kernel) ------------------
     peak = None
     if rank == 0:
-        arms = (ctypes.c_double * 5)()
+        arms = (ctypes.c_double * 7)()
         cabi.check(L.tb_int_peak_detail(arms))
         peak = dict(imad_only=arms[0], lop3_only=arms[1], add_only=arms[2], imad_add=arms[3], imad_lop3=arms[4])
+        fp64_arms = dict(dfma_only=arms[5], dfma_imad_lop3=arms[6])
     kms = sorted(kernel_ms)[len(kernel_ms) // 2]
     rms = sorted(rows_ms)[len(rows_ms) // 2]
 
@@ -486,7 +488,7 @@ def main():
                         int32_ops_per_neighbor=w32, peak_source="tb_int_peak_detail microbenchmark, measured in this run: best of five "
                         "arms of single-SASS-instruction chains on all SMs, operations counted per instruction; "
                         "nominal = SMs x 4 schedulers x 32 lanes x SM clock (one warp instruction per scheduler per clock)",
-                        peak_detail=peak,
+                        peak_detail=peak, fp64_issue_arms=fp64_arms,
                         hbm=dict(achieved=hbm_achieved, peak=hbm_peak, unit="GB/s", frac=hbm_achieved / hbm_peak,
                                  peak_source="MEASURED_PEAKS.json" if peaks_file.exists() else "fallback"))
         cpu = None

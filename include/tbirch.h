@@ -247,9 +247,10 @@ void tb_modkernel_destroy(tb_modkernel *k);
 /* Measures the int32 issue peak used as the roofline denominator: unrolled chains of single
  * SASS instructions on every SM, counted per instruction.  Returns int32 op/s for
  * out[0] IMAD only (fma pipe), out[1] LOP3 only (alu pipe), out[2] ADD only (ptxas splits them
- * over both pipes), out[3] IMAD + ADD alternating, out[4] IMAD + LOP3 alternating.  The nominal
- * bound of the two-pipe arms is the issue slot: SMs x 4 x 32 x clock. */
-int tb_int_peak_detail(double out[5]);
+ * over both pipes), out[3] IMAD + ADD alternating, out[4] IMAD + LOP3 alternating, out[5] DFMA
+ * only (fp64 pipe), out[6] DFMA + IMAD + LOP3 in turn (instructions/s, all three pipes).  The nominal
+ * bound of the multi-pipe arms is the issue slot: SMs x 4 x 32 x clock. */
+int tb_int_peak_detail(double out[7]);
 /* The same, condensed: fma-pipe-only, alu-pipe-only, and the best two-pipe arm. */
 int tb_int_peak(double *imad_ops_per_s, double *alu_ops_per_s, double *mixed_ops_per_s);
 

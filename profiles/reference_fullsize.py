@@ -13,7 +13,10 @@ sys.path.insert(0, str(ROOT))
 import bench  # noqa: E402
 
 cores = os.cpu_count() or 1
-n = min(cores, 16)
+# each full-size process holds its T_p as growing std::vector<int>s (3.6 GB of CSR, ~10 GB at the peak of a
+# reallocation): as many processes as the host's free memory allows, 16 at most
+avail_gb = next(int(l.split()[1]) for l in open("/proc/meminfo") if l.startswith("MemAvailable")) / 1e6
+n = max(1, min(cores, 16, int(avail_gb // 12)))
 big = [9973, 9967, 9949, 9941, 9931, 9929, 9923, 9907, 9901, 9887, 9883, 9871, 9859, 9857, 9851, 9839][:n]
 t0 = time.time()
 neighbors, slowest, kind = bench.reference_sample(big, timeout=3000)

@@ -62,7 +62,7 @@ enum_kernel(const __grid_constant__ GenusCtx gc, const __grid_constant__ PrimeCt
     Form<C128> nq;
     Iso<C128> s;
     build_neighbor(q, vx, vy, vz, 0, pc, nq, s);
-    const bool ok = reduce_neighbor(nq, s, pc.fp64_reduce != 0);
+    const bool ok = reduce_neighbor(nq, s, pc.fp64_reduce != 0, false);
     bool fits = nq.a.fits_i64() && nq.b.fits_i64() && nq.c.fits_i64() && nq.f.fits_i64() && nq.g.fits_i64() &&
                 nq.h.fits_i64() && s.a11.fits_i64() && s.a12.fits_i64() && s.a13.fits_i64() && s.a21.fits_i64() &&
                 s.a22.fits_i64() && s.a23.fits_i64() && s.a31.fits_i64() && s.a32.fits_i64() && s.a33.fits_i64();
@@ -88,7 +88,7 @@ __global__ void reduce_form_kernel(i64 *form /* in/out [6] */, i64 *status)
     s.a11 = C128(1); s.a12 = C128(0); s.a13 = C128(0);
     s.a21 = C128(0); s.a22 = C128(1); s.a23 = C128(0);
     s.a31 = C128(0); s.a32 = C128(0); s.a33 = C128(1);
-    const bool ok = reduce_neighbor(q, s, false);
+    const bool ok = reduce_neighbor(q, s, false, false);
     if (threadIdx.x == 0)
     {
         form[0] = q.a.low64(); form[1] = q.b.low64(); form[2] = q.c.low64();

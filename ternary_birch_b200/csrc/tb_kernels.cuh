@@ -13,6 +13,18 @@
 // in registers and the genus table is a few MB of random 128-byte lines).
 #pragma once
 
+// compute-sanitizer is closed on the GPU pool this was developed on, so the memory-safety evidence is a
+// second build with -DTB_DEBUG_BOUNDS: every computed shared-memory index and every global output
+// position of the row kernels (and the table index of the lookup) is asserted before use, a violation
+// traps the kernel ("device-side assert triggered" -> the call fails), and the GPU test-suite is run
+// against that build (profiles/run_bounds_build.sh).
+#ifdef TB_DEBUG_BOUNDS
+#include <cassert>
+#define TB_CHECK(cond) assert(cond)
+#else
+#define TB_CHECK(cond) ((void)0)
+#endif
+
 #include "tb_neighbor.cuh"
 
 namespace tb {
@@ -317,6 +329,9 @@ struct RowLaunch {
     int *maxmult;          // max number of neighbors of one row in one class = max |entry| (narrow read-back)
     u32 *scratch;          // global-memory stand-in for the per-row shared-memory state when it does not fit one SM:
     size_t scratch_words;  //   one slot of scratch_words per CTA, and each CTA then walks several rows
+    i64 extent;            // entries allocated for data / indices (bounds checks of the debug build)
+    const unsigned char *incl;   // [ceil(2^K / 8)][N] bit kk: lut[8 c + kk][n] != -1   (rows_acc_kernel)
+    int *overflow;         // set when a class is hit 256 times or more (rows_acc_kernel; the host falls back)
     unsigned short *idx16; // optional narrow twins of indices / data for the read-back over PCIe
     signed char *dat8;     //   (valid when every dim <= 65536 and maxmult <= 127), same offsets
     int *data;
@@ -392,6 +407,7 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
         u32 r = Wrow[t] >> L.K;
         if (r >= (u32)L.N) continue;
         int j = wprefix[r >> 5] + __popc(mask[r >> 5] & ((1u << (r & 31)) - 1u));
+        TB_CHECK(j >= 0 && j < maxcols);
         atomicAdd(&start[j + 1], 1);
     }
     // column -> representative
@@ -427,6 +443,7 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
         if (r >= (u32)L.N) continue;
         int j = wprefix[r >> 5] + __popc(mask[r >> 5] & ((1u << (r & 31)) - 1u));
         int slot = atomicSub(&start[j + 1], 1) - 1;
+        TB_CHECK(j >= 0 && j < maxcols && slot >= 0 && slot < (int)L.P1);
         spins[slot] = (unsigned short)(w & spin_mask);
     }
     __syncthreads();
@@ -567,6 +584,7 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
                     if (pass == 1 && value != 0)
                     {
                         const i64 at = wbase[kk] + cnt[kk] + __popc(ballot & ((1u << lane) - 1u));
+                        TB_CHECK(at >= 0 && at < L.extent && rpos >= 0);
                         if (L.data)
                         {
                             L.data[at] = value;
@@ -631,6 +649,251 @@ __global__ void __launch_bounds__(512, 2) rows_kernel(const __grid_constant__ Ro
     }
     if (!SCRATCH) break;         // shared-memory form: one row per CTA
     __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// rows_acc_kernel: the row phase for the common case (every class of a row is hit fewer than
+// 256 times), single pass like rows_kernel<ROWS_FUSED> but without the counting sort.
+//
+// A Hecke row entry is  run - 2 * #{neighbors of the class with chi_k = -1}, so all a row needs
+// per touched class is a handful of small counters -- and those are accumulated directly with
+// shared-memory atomics while the packed words stream by, instead of first sorting the spins
+// into runs and then walking the runs (ncu, profiles/r1k: 75 % of rows_kernel's instructions sat
+// in that walk and in its two-sweep compaction).  Per row, one CTA:
+//   A  mask[r]      bitmask of the classes hit (atomicOr), rank of a class = popcount prefix
+//   C  acc[rank]    two 32-bit words of 4 byte-counters each: for the 8 conductors of the
+//                   current chunk, how many neighbors of the class have chi = -1; byte 0 of
+//                   chunk 0 (conductor index 0: chi = +1 always) counts the run itself
+//   D  mask words in order (lane = bit = class): counters -> entries -> ballots; a count sweep
+//      gives every warp its offset per conductor, a second sweep stores (uint16 column + int8
+//      entry, or int32 pairs).  Rows chain through the same decoupled look-back.
+// More than 8 conductors: C and D repeat per chunk of 8 (the row's words are L2-resident).
+// A class hit 256 times or more overflows its run counter: the kernel raises *overflow and
+// the host redoes the row phase with rows_kernel.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ u64 parity_bytes(u32 spin, int kc)
+{
+    u64 v = 0;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) v |= (u64)(__popc(spin & (u32)(kc + kk)) & 1) << (8 * kk);
+    return v;
+}
+
+__global__ void __launch_bounds__(512, 2) rows_acc_kernel(const __grid_constant__ RowLaunch L)
+{
+    extern __shared__ u32 smem[];
+    // layout: mask[mw] | wprefix[mw] | acc_lo[maxcols] | acc_hi[maxcols] | warp_cnt[8][32] | runlen (u8)[maxcols]
+    const int mw = L.mask_words;
+    const int maxcols = min((int)L.P1, L.N);
+    u32 *mask = smem;
+    u32 *wprefix = mask + mw;
+    u32 *acc_lo = wprefix + mw;
+    u32 *acc_hi = acc_lo + maxcols;
+    int *warp_cnt = (int *)(acc_hi + maxcols);
+    unsigned char *runlen = (unsigned char *)(warp_cnt + 8 * 32 + 40);
+    int *scan_tmp = warp_cnt;                                  // block_exclusive_scan scratch (40 ints), before phase D
+
+    __shared__ int s_row;
+    __shared__ i64 s_base[8];
+    __shared__ int s_npos[8];
+    __shared__ u64 s_partab[1024];
+    __shared__ int s_maxrun;
+
+    // rows are taken in ticket order: every row a CTA waits on in the look-back belongs to a CTA
+    // that is already running or finished
+    if (threadIdx.x == 0) { s_row = atomicAdd(L.ticket, 1); s_maxrun = 0; }
+    __syncthreads();
+    const int lrow = s_row;
+    if (lrow >= L.rows) return;
+    const int n = L.rep_begin + lrow;
+    const u32 *Wrow = L.W + (size_t)lrow * L.P1;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, w = tid >> 5, nw = nt >> 5;
+    const u32 spin_mask = (1u << L.K) - 1u;
+    const int C = 1 << L.K;
+    const bool use_tab = L.K <= 10;
+    const u32 lt = (1u << lane) - 1u;
+
+    // ---- A: classes hit --------------------------------------------------------
+    for (int i = tid; i < mw; i += nt) mask[i] = 0u;
+    __syncthreads();
+    for (u32 t = tid; t < L.P1; t += nt)
+    {
+        const u32 r = Wrow[t] >> L.K;                          // a failed neighbor carries 0xffffffff: r >= N, skipped
+        if (r < (u32)L.N) atomicOr(&mask[r >> 5], 1u << (r & 31));
+    }
+    __syncthreads();
+    int carry = 0;
+    for (int base = 0; base < mw; base += nt)
+    {
+        const int i = base + tid;
+        const int c = i < mw ? __popc(mask[i]) : 0;
+        int total;
+        const int ex = block_exclusive_scan(c, scan_tmp, total);
+        if (i < mw) wprefix[i] = carry + ex;
+        carry += total;
+    }
+    const int ncols = carry;
+
+    // this warp's block of mask words (so of ranks, so of output positions): contiguous, ascending
+    const int wpw = (mw + nw - 1) / nw;
+    const int ibeg = min(mw, w * wpw), iend = min(mw, ibeg + wpw);
+
+    for (int kc = 0; kc < C; kc += 8)
+    {
+        const int nk = min(8, C - kc);
+        const bool both = nk > 4;
+        __syncthreads();
+        // ---- C: counters ---------------------------------------------------------
+        for (int j = tid; j < ncols; j += nt) { acc_lo[j] = 0u; acc_hi[j] = 0u; }
+        if (tid < 8) s_npos[tid] = tid < nk ? L.lut[(size_t)(kc + tid) * L.N + n] : -1;
+        if (use_tab)
+            for (int sp = tid; sp < C; sp += nt) s_partab[sp] = parity_bytes((u32)sp, kc) | (kc == 0 ? 1ull : 0ull);
+        __syncthreads();
+        for (u32 t = tid; t < L.P1; t += nt)
+        {
+            const u32 word = Wrow[t];
+            const u32 r = word >> L.K;
+            if (r >= (u32)L.N) continue;
+            const u32 sp = word & spin_mask;
+            const int j = wprefix[r >> 5] + __popc(mask[r >> 5] & ((1u << (r & 31)) - 1u));
+            TB_CHECK(j >= 0 && j < ncols && ncols <= maxcols);
+            const u64 add = use_tab ? s_partab[sp] : (parity_bytes(sp, kc) | (kc == 0 ? 1ull : 0ull));
+            const u32 old = atomicAdd(&acc_lo[j], (u32)add);
+            if (kc == 0 && (old & 0xffu) == 0xffu) *L.overflow = 1;         // 256th neighbor of one class
+            if (both && (u32)(add >> 32)) atomicAdd(&acc_hi[j], (u32)(add >> 32));
+        }
+        __syncthreads();
+        if (kc == 0 && C > 8)
+            for (int j = tid; j < ncols; j += nt) runlen[j] = (unsigned char)(acc_lo[j] & 0xffu);
+
+        // ---- D: entries, ascending columns, zeros dropped -----------------------------
+        int cnt[8];
+        i64 wbase[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) { cnt[kk] = 0; wbase[kk] = 0; }
+        int mx = 0;
+        for (int pass = 0; pass < 2; ++pass)
+        {
+            for (int i = ibeg; i < iend; ++i)
+            {
+                const u32 m = mask[i];
+                const bool hit = (m >> lane) & 1u;
+                const int j = wprefix[i] + __popc(m & lt);
+                const int r = i * 32 + lane;
+                u32 lo = 0u, hi = 0u, run = 0u, inc = 0u;
+                if (hit)
+                {
+                    TB_CHECK(j >= 0 && j < ncols && r < L.N);
+                    lo = acc_lo[j];
+                    hi = both ? acc_hi[j] : 0u;
+                    run = kc == 0 ? (lo & 0xffu) : (u32)runlen[j];
+                    if (kc == 0) lo &= ~0xffu;
+                    inc = L.incl[(size_t)(kc >> 3) * L.N + r];           // bit kk: lut[kc + kk][r] != -1
+                }
+                if (pass == 0)
+                {
+                    mx = max(mx, (int)run);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                    {
+                        if (kk >= nk) break;
+                        const u32 odd = ((kk < 4 ? lo : hi) >> (8 * (kk & 3))) & 0xffu;
+                        const bool nz = hit && ((inc >> kk) & 1u) && (2u * odd != run);
+                        cnt[kk] += __popc(__ballot_sync(0xffffffffu, nz));
+                    }
+                }
+                else
+                {
+                    int rp[8];
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) rp[kk] = -1;
+                    if (hit && inc)
+                    {
+                        const int *src = L.lutT + ((size_t)r << L.K) + kc;
+                        if (nk == 8)
+                        {
+                            const int4 x = __ldg(reinterpret_cast<const int4 *>(src));
+                            const int4 y = __ldg(reinterpret_cast<const int4 *>(src) + 1);
+                            rp[0] = x.x; rp[1] = x.y; rp[2] = x.z; rp[3] = x.w;
+                            rp[4] = y.x; rp[5] = y.y; rp[6] = y.z; rp[7] = y.w;
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int kk = 0; kk < 8; ++kk) if (kk < nk) rp[kk] = __ldg(src + kk);
+                        }
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                    {
+                        if (kk >= nk || s_npos[kk] == -1) continue;                  // Genus.h:624-625 (warp-uniform)
+                        const u32 odd = ((kk < 4 ? lo : hi) >> (8 * (kk & 3))) & 0xffu;
+                        const int value = (int)run - 2 * (int)odd;
+                        const bool nz = hit && rp[kk] != -1 && value != 0;
+                        const unsigned ballot = __ballot_sync(0xffffffffu, nz);
+                        if (nz)
+                        {
+                            const i64 at = wbase[kk] + cnt[kk] + __popc(ballot & lt);
+                            TB_CHECK(at >= 0 && at < L.extent && rp[kk] >= 0);
+                            if (L.idx16) { L.idx16[at] = (unsigned short)rp[kk]; L.dat8[at] = (signed char)value; }
+                            else { L.data[at] = value; L.indices[at] = rp[kk]; }
+                        }
+                        cnt[kk] += __popc(ballot);
+                    }
+                }
+            }
+            if (pass == 1) break;
+            // per-warp totals -> this row's totals -> chained offsets
+            if (lane == 0)
+            {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) warp_cnt[kk * 32 + w] = cnt[kk];
+            }
+            if (kc == 0)
+            {
+                for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                if (lane == 0 && mx > s_maxrun) atomicMax(&s_maxrun, mx);
+            }
+            __syncthreads();
+            if (tid < nk)
+            {
+                const int k = kc + tid;
+                i64 total = 0;
+                if (s_npos[tid] != -1)
+                    for (int ww = 0; ww < nw; ++ww) total += warp_cnt[tid * 32 + ww];
+                u64 *state = L.lookback + (size_t)k * L.rows;
+                const u64 FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VALUE = (1ull << 62) - 1;
+                if (lrow > 0) atomicExch(state + lrow, FLAG_AGG | (u64)total);
+                i64 excl = 0;
+                for (int j = lrow - 1; j >= 0; )
+                {
+                    const u64 v = *(volatile u64 *)(state + j);
+                    const u64 flag = v >> 62;
+                    if (flag == 0) continue;                 // predecessor still counting
+                    excl += (i64)(v & VALUE);
+                    if (flag == 2) break;                    // inclusive prefix: done
+                    --j;
+                }
+                const i64 incl_total = excl + total;
+                atomicExch(state + lrow, FLAG_INC | (u64)incl_total);
+                s_base[tid] = L.nnzbase[k] + excl;
+                if (s_npos[tid] != -1)
+                    (L.indptr_all + L.rowbase[k])[s_npos[tid] - L.rowfirst[k] + 1] = (int)incl_total;
+                if (lrow == L.rows - 1) L.nnz_out[k] = incl_total;
+            }
+            if (kc == 0 && tid == 32 && L.maxmult && s_maxrun > *(volatile int *)L.maxmult) atomicMax(L.maxmult, s_maxrun);
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+            {
+                int before = 0;
+                for (int ww = 0; ww < w; ++ww) before += warp_cnt[kk * 32 + ww];
+                wbase[kk] = s_base[kk] + before;
+                cnt[kk] = 0;
+            }
+        }
     }
 }
 
@@ -749,15 +1012,21 @@ __global__ void eigen_dot_kernel(const u32 *W, u32 P1, int K, int N, const int *
 //   KIND 2  ADD only: ptxas itself splits these between IADD3 (alu) and IMAD.IADD (fma)
 //   KIND 3  IMAD and ADD alternating
 //   KIND 4  IMAD and LOP3 alternating
+//   KIND 5  DFMA only                      (fp64 pipe)
+//   KIND 6  DFMA, IMAD and LOP3 in turn    (three pipes: does a DFMA cost more than one issue slot?)
 // KIND 2-4 use both pipes and are bounded by the issue slot (1 warp instruction/clk/SMSP =
 // 148 x 4 x 32 x 1.965 GHz = 37.2 T int32-op/s nominal).  16 independent chains per thread.
+// The reduce loop of neighbors_kernel is half DFMA/DADD/DSETP, so KIND 5-6 say what the issue
+// slot can deliver for THAT mix.
 // ---------------------------------------------------------------------------
+#define TB_PEAK_DFMA(z) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(z) : "d"(dm), "d"(dc))
 #define TB_PEAK_IMAD(y) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(y) : "r"(m), "r"(c))
 #define TB_PEAK_ADD(x, z) asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(z))
 #define TB_PEAK_LOP(x, z) asm volatile("lop3.b32 %0, %0, %1, %2, 0x78;" : "+r"(x) : "r"(z), "r"(m))
 #define TB_PEAK_UNROLL 16          /* steps per loop iteration */
 #define TB_PEAK_OPS_SINGLE 8       /* instructions per step, KIND 0-2 */
 #define TB_PEAK_OPS_MIXED 16       /* instructions per step, KIND 3-4 */
+#define TB_PEAK_OPS_TRIPLE 24      /* instructions per step, KIND 6 */
 
 template <int KIND>
 __global__ void __launch_bounds__(256) int_peak_kernel(u32 *sink, int iters, u32 seed)
@@ -766,12 +1035,26 @@ __global__ void __launch_bounds__(256) int_peak_kernel(u32 *sink, int iters, u32
     u32 x4 = x0 * 11u + 4u, x5 = x0 * 13u + 5u, x6 = x0 * 17u + 6u, x7 = x0 * 19u + 7u;
     u32 y0 = x0 ^ 1u, y1 = x1 ^ 2u, y2 = x2 ^ 3u, y3 = x3 ^ 4u, y4 = x4 ^ 5u, y5 = x5 ^ 6u, y6 = x6 ^ 7u, y7 = x7 ^ 8u;
     const u32 m = seed | 1u, c = seed ^ 0x9e3779b9u;
+    double z0 = (double)x0, z1 = (double)x1, z2 = (double)x2, z3 = (double)x3, z4 = (double)x4, z5 = (double)x5, z6 = (double)x6, z7 = (double)x7;
+    const double dm = 1.0 - 1.0 / (double)(seed | 1u), dc = (double)(seed & 7u);
 #pragma unroll 1
     for (int i = 0; i < iters; ++i)
     {
 #pragma unroll
         for (int u = 0; u < TB_PEAK_UNROLL; ++u)
         {
+            if (KIND == 5)
+            {
+                TB_PEAK_DFMA(z0); TB_PEAK_DFMA(z1); TB_PEAK_DFMA(z2); TB_PEAK_DFMA(z3);
+                TB_PEAK_DFMA(z4); TB_PEAK_DFMA(z5); TB_PEAK_DFMA(z6); TB_PEAK_DFMA(z7);
+            }
+            if (KIND == 6)
+            {
+                TB_PEAK_DFMA(z0); TB_PEAK_IMAD(y0); TB_PEAK_LOP(x0, x1); TB_PEAK_DFMA(z1); TB_PEAK_IMAD(y1); TB_PEAK_LOP(x1, x2);
+                TB_PEAK_DFMA(z2); TB_PEAK_IMAD(y2); TB_PEAK_LOP(x2, x3); TB_PEAK_DFMA(z3); TB_PEAK_IMAD(y3); TB_PEAK_LOP(x3, x4);
+                TB_PEAK_DFMA(z4); TB_PEAK_IMAD(y4); TB_PEAK_LOP(x4, x5); TB_PEAK_DFMA(z5); TB_PEAK_IMAD(y5); TB_PEAK_LOP(x5, x6);
+                TB_PEAK_DFMA(z6); TB_PEAK_IMAD(y6); TB_PEAK_LOP(x6, x7); TB_PEAK_DFMA(z7); TB_PEAK_IMAD(y7); TB_PEAK_LOP(x7, x0);
+            }
             if (KIND == 0)
             {
                 TB_PEAK_IMAD(y0); TB_PEAK_IMAD(y1); TB_PEAK_IMAD(y2); TB_PEAK_IMAD(y3);
@@ -804,6 +1087,7 @@ __global__ void __launch_bounds__(256) int_peak_kernel(u32 *sink, int iters, u32
         }
     }
     u32 r = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7 ^ y0 ^ y1 ^ y2 ^ y3 ^ y4 ^ y5 ^ y6 ^ y7;
+    r ^= (u32)__double2hiint(((z0 + z1) + (z2 + z3)) + ((z4 + z5) + (z6 + z7)));
     if (r == 0x12345678u) sink[0] = r;
 }
 

@@ -12,6 +12,10 @@
 
 #include "tb_int.cuh"
 
+#ifndef TB_CHECK            /* defined by tb_kernels.cuh: assert under -DTB_DEBUG_BOUNDS, nothing otherwise */
+#define TB_CHECK(cond) ((void)0)
+#endif
+
 namespace tb {
 
 // ---------------------------------------------------------------------------
@@ -38,7 +42,9 @@ struct PrimeCtx {
     u32 fp64_reduce;  // host-verified: isometry entries stay below 2^52 in the FP64 reduce loop
     u32 m32;          // floor(2^32 / p) when p < 2^16 (32-bit Barrett), else 0
     u32 narrow_trace; // two-limb modes: composed isometry / denominator proven below 2^61 (64-bit trace)
-    u32 pad2;
+    u32 proven_small; // every value build_neighbor hands to the reduction is proven below 2^50 (no per-lane test)
+    u32 iso32;        // 64-bit modes: table isometries and reduced neighbor isometries proven below 2^31 (32-bit products)
+    u32 pad3;
     u64 pp;
     InvDiv dp;        // division by p
     InvDiv dpp;       // division by p^2
@@ -394,7 +400,7 @@ __device__ __forceinline__ Z shear_quotient(Z a, Z h)
 }
 
 template <class Z>
-__device__ __forceinline__ bool eisenstein_reduce(Form<Z> &q, Iso<Z> &s)
+__device__ __noinline__ bool eisenstein_reduce(Form<Z> &q, Iso<Z> &s)
 {
     Z a = q.a, b = q.b, c = q.c, f = q.f, g = q.g, h = q.h;
     Z t;
@@ -574,14 +580,24 @@ __device__ __forceinline__ bool eisenstein_reduce(Form<Z> &q, Iso<Z> &s)
 // The operation order is the reference's (QuadForm.h:540-691), so the isometry
 // is bit-identical.
 // ---------------------------------------------------------------------------
+// 1 / d to ~2^-36 relative: the hardware's ~20-bit seed and ONE Newton step.  That is all the shear
+// quotients need: on a positive definite form |h| < 2 sqrt(ab), |f| < 2 sqrt(bc), |g| < 2 sqrt(ac), so
+// with coefficients below 2^50 every quotient (a-h)/2a, (b-f)/2b, (a-g)/2a is below 2^26 in magnitude
+// and its estimate is within 2^-10 of the true value -- dshear_t's exact remainder then decides
+// between floor and floor + 1.  (TB_RCP_STEPS=2 restores the second step for A/B timing.)
+#ifndef TB_RCP_STEPS
+#define TB_RCP_STEPS 1
+#endif
 __device__ __forceinline__ double rcp_f64(double d)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
     double e = fma(-d, r, 1.0);
     r = fma(r, e, r);
+#if TB_RCP_STEPS > 1
     e = fma(-d, r, 1.0);
     r = fma(r, e, r);
+#endif
     return r;
 }
 // x with its sign bit XORed by m (m = 0 or 0x80000000): one LOP3
@@ -654,7 +670,10 @@ __device__ __forceinline__ int reduce_loop_fp64(DReduce &d)
         if (++iters > TB_REDUCE_CAP) break;
 
         // a + b + f + g + h < 0                                      542-549
+        // (some lane of nearly every trip needs it, so it runs unconditionally with a 0/1 multiplier
+        //  instead of under a vote and a divergent branch)
         {
+#ifdef TB_FIX_BRANCHY
             const bool fix = active && sum < 0.0;
             if (__any_sync(warp, fix))
             {
@@ -668,6 +687,16 @@ __device__ __forceinline__ int reduce_loop_fp64(DReduce &d)
                     g += h + (a + a);
                 }
             }
+#else
+            const double fm = (active && sum < 0.0) ? 1.0 : 0.0;
+            const double m13 = xflip(fm, sg1 ^ sg3), m23 = xflip(fm, sg2 ^ sg3);
+            s13 = fma(m23, s12, fma(m13, s11, s13));
+            s23 = fma(m23, s22, fma(m13, s21, s23));
+            s33 = fma(m23, s32, fma(m13, s31, s33));
+            c = fma(fm, sum, c);
+            f = fma(fm, h + (b + b), f);
+            g = fma(fm, h + (a + a), g);
+#endif
         }
 
         // shear 1: col2 += t col1                                    551-567
@@ -770,9 +799,12 @@ __device__ __forceinline__ int reduce_loop_fp64(DReduce &d)
     return iters;
 }
 
-// Post-loop boundary fix-ups (QuadForm.h:693-764): rare, so plain branches.
+// Post-loop boundary fix-ups (QuadForm.h:693-764): rare, so plain branches, and out of line: the
+// hot path only asks whether the form lies on a boundary of the reduction domain at all
+// (on_boundary), which is the first clause of each of the ten fix-ups -- when none holds for the
+// form as the loop left it, none of them fires and nothing changes.
 template <class Z>
-__device__ __forceinline__ void reduce_boundary(Form<Z> &q, Iso<Z> &s)
+__device__ __noinline__ void reduce_boundary(Form<Z> &q, Iso<Z> &s)
 {
     Z a = q.a, b = q.b, c = q.c, f = q.f, g = q.g, h = q.h, t;
     const Z zero = Z(0);
@@ -796,18 +828,36 @@ __device__ __forceinline__ void reduce_boundary(Form<Z> &q, Iso<Z> &s)
     q.a = a; q.b = b; q.c = c; q.f = f; q.g = g; q.h = h;
 }
 
+// The integer loop lives out of line (it is the fallback); copies keep the caller's state in registers.
+template <class Z>
+__device__ __forceinline__ bool reduce_out_of_line(Form<Z> &q, Iso<Z> &s)
+{
+    Form<Z> tq = q;
+    Iso<Z> ts = s;
+    const bool ok = eisenstein_reduce(tq, ts);
+    q = tq;
+    s = ts;
+    return ok;
+}
+
 // Reduction entry point of the kernels: FP64 loop when the launch allows it and
 // the whole warp's operands are small, else the integer code.  Every lane of the
 // warp must call this (it votes).
 template <class Z>
-__device__ __forceinline__ bool reduce_neighbor(Form<Z> &q, Iso<Z> &s, bool fp64_allowed)
+__device__ __forceinline__ bool reduce_neighbor(Form<Z> &q, Iso<Z> &s, bool fp64_allowed, bool proven_small)
 {
-    bool small = fits50(q.a) && fits50(q.b) && fits50(q.c) && fits50(q.f) && fits50(q.g) && fits50(q.h) &&
-                 fits50(s.a11) && fits50(s.a12) && fits50(s.a13) && fits50(s.a21) && fits50(s.a22) &&
-                 fits50(s.a23) && fits50(s.a31) && fits50(s.a32) && fits50(s.a33) &&
-                 q.a > Z(0) && q.b > Z(0);
-    __syncwarp(0xffffffffu);
-    if (!(fp64_allowed && __all_sync(0xffffffffu, small))) return eisenstein_reduce(q, s);
+    // proven_small: the host bounded everything build_neighbor can hand over below 2^50 for this launch
+    // (PrimeCtx::proven_small), so the per-lane magnitude test and its vote are skipped
+    if (!proven_small)
+    {
+        bool small = fits50(q.a) && fits50(q.b) && fits50(q.c) && fits50(q.f) && fits50(q.g) && fits50(q.h) &&
+                     fits50(s.a11) && fits50(s.a12) && fits50(s.a13) && fits50(s.a21) && fits50(s.a22) &&
+                     fits50(s.a23) && fits50(s.a31) && fits50(s.a32) && fits50(s.a33) &&
+                     q.a > Z(0) && q.b > Z(0);
+        __syncwarp(0xffffffffu);
+        if (!(fp64_allowed && __all_sync(0xffffffffu, small))) return reduce_out_of_line(q, s);
+    }
+    else if (!fp64_allowed) return reduce_out_of_line(q, s);
 
     DReduce d;
     d.a = __ll2double_rn(q.a.low64()); d.b = __ll2double_rn(q.b.low64()); d.c = __ll2double_rn(q.c.low64());
@@ -816,12 +866,23 @@ __device__ __forceinline__ bool reduce_neighbor(Form<Z> &q, Iso<Z> &s, bool fp64
     d.s21 = __ll2double_rn(s.a21.low64()); d.s22 = __ll2double_rn(s.a22.low64()); d.s23 = __ll2double_rn(s.a23.low64());
     d.s31 = __ll2double_rn(s.a31.low64()); d.s32 = __ll2double_rn(s.a32.low64()); d.s33 = __ll2double_rn(s.a33.low64());
     const int iters = reduce_loop_fp64(d);
+    // on a boundary of the reduction domain?  (first clauses of QuadForm.h:693, 702, 710, 718, 726, 732,
+    // 738, 744, 752; 759 repeats 744)
+    const bool on_boundary = ((((d.a + d.b) + d.f) + d.g) + d.h == 0.0) | (d.a == -d.h) | (d.a == -d.g) | (d.b == -d.f) |
+                             (d.a == d.h) | (d.a == d.g) | (d.b == d.f) | (d.a == d.b) | (d.b == d.c);
     q.a = Z(__double2ll_rn(d.a)); q.b = Z(__double2ll_rn(d.b)); q.c = Z(__double2ll_rn(d.c));
     q.f = Z(__double2ll_rn(d.f)); q.g = Z(__double2ll_rn(d.g)); q.h = Z(__double2ll_rn(d.h));
     s.a11 = Z(__double2ll_rn(d.s11)); s.a12 = Z(__double2ll_rn(d.s12)); s.a13 = Z(__double2ll_rn(d.s13));
     s.a21 = Z(__double2ll_rn(d.s21)); s.a22 = Z(__double2ll_rn(d.s22)); s.a23 = Z(__double2ll_rn(d.s23));
     s.a31 = Z(__double2ll_rn(d.s31)); s.a32 = Z(__double2ll_rn(d.s32)); s.a33 = Z(__double2ll_rn(d.s33));
-    reduce_boundary(q, s);
+    if (on_boundary)
+    {
+        Form<Z> tq = q;          // copies: only these are address-taken by the out-of-line call
+        Iso<Z> ts = s;
+        reduce_boundary(tq, ts);
+        q = tq;
+        s = ts;
+    }
     return iters <= TB_REDUCE_CAP;
 }
 
@@ -851,6 +912,7 @@ __device__ __forceinline__ int genus_lookup(const Form<Z> &q, const GenusCtx &gc
     {
         const int idx = __ldg(gc.slots + slot);
         if (idx < 0) break;
+        TB_CHECK(idx < gc.N);
         const longlong2 *key = reinterpret_cast<const longlong2 *>(gc.rep + (size_t)idx * TB_REC_WORDS);
         const longlong2 x = __ldg(key), y = __ldg(key + 1), z = __ldg(key + 2);
         if (x.x == k0 && x.y == k1 && y.x == k2 && y.y == k3 && z.x == k4 && z.y == k5) { found = idx; break; }
@@ -1026,7 +1088,7 @@ __device__ __forceinline__ int one_neighbor(int n, u32 t, const RepPrime &rp, co
         o.s.a21 = zero; o.s.a22 = one; o.s.a23 = zero;
         o.s.a31 = zero; o.s.a32 = zero; o.s.a33 = one;
     }
-    if (!reduce_neighbor(o.q, o.s, pc.fp64_reduce != 0)) status = NBR_OVERFLOW;
+    if (!reduce_neighbor(o.q, o.s, pc.fp64_reduce != 0, pc.proven_small != 0)) status = NBR_OVERFLOW;
 
     int r = genus_lookup(o.q, gc);                           // Genus.h:575
     if (r < 0)
@@ -1065,6 +1127,34 @@ __device__ __forceinline__ int one_neighbor(int n, u32 t, const RepPrime &rp, co
         if (tr64 != -den64)
         {
             o.spin = prime_parities(tr64 + den64, gc);
+            return status;
+        }
+    }
+    if (!IsWide<Z>::value && pc.iso32 && !want_comp)
+    {
+        // 64-bit modes under PrimeCtx::iso32: every factor of cur.s * s * rep.sinv fits 32 bits, so the trace
+        //     tr = sum_{k,j} s[k][j] * X[j][k],   X = rep.sinv * cur.s
+        // is 27 32x32->64 multiply-adds for X and nine 64x32 ones for the sum (ring arithmetic modulo 2^64,
+        // exactly what the 64-bit products below compute, at half the instructions)
+        int cs[9], ri[9], sv[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { cs[i] = (int)__ldg(cur + 7 + i); ri[i] = (int)__ldg(rep + 7 + i); }
+        sv[0] = (int)o.s.a11.low64(); sv[1] = (int)o.s.a12.low64(); sv[2] = (int)o.s.a13.low64();
+        sv[3] = (int)o.s.a21.low64(); sv[4] = (int)o.s.a22.low64(); sv[5] = (int)o.s.a23.low64();
+        sv[6] = (int)o.s.a31.low64(); sv[7] = (int)o.s.a32.low64(); sv[8] = (int)o.s.a33.low64();
+        u64 tr = 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+            {
+                const i64 X = (i64)ri[3 * j] * cs[k] + (i64)ri[3 * j + 1] * cs[3 + k] + (i64)ri[3 * j + 2] * cs[6 + k];
+                tr += (u64)X * (u64)(i64)sv[3 * k + j];
+            }
+        const u64 den = (u64)pc.p * (u64)__ldg(cur + 6) * (u64)__ldg(rep + 6);
+        if (tr != 0ull - den)                                // Spinor.h:21-25
+        {
+            o.spin = prime_parities(Z((i64)(tr + den)), gc);
             return status;
         }
     }

@@ -263,16 +263,20 @@ struct ReadbackPolicy {
     double rate[2] = {0.0, 0.0};      // running delivered GB/s of int32 CSR per format
     int samples[2] = {0, 0};
     int current = NARROW;
-    uint64_t decisions = 0;
+    int since_probe = 0;              // read-backs measured since the other format was last tried
+    int pending_probe = 0;            // a probe of the other format has been handed out and not measured yet
 
     int choose()
     {
         std::lock_guard<std::mutex> lk(mx);
-        ++decisions;
-        if (samples[NARROW] < 2) return NARROW;
-        if (samples[PLAIN] < 2) return PLAIN;
+        if (samples[NARROW] == 0) return NARROW;          // one measured read-back of each format first
+        if (samples[PLAIN] == 0) return PLAIN;
         if (rate[1 - current] > 1.15 * rate[current]) current = 1 - current;   // hysteresis: ranks adapt concurrently
-        if (decisions % 24 == 0) return 1 - current;                           // the host's load changes: look again
+        if (since_probe >= 32 && !pending_probe)          // the host's load changes: look at the other format again
+        {
+            pending_probe = 1;
+            return 1 - current;
+        }
         return current;
     }
     void record(int format, double csr_bytes, double seconds)
@@ -282,6 +286,8 @@ struct ReadbackPolicy {
         const double r = csr_bytes / seconds / 1e9;
         rate[format] = samples[format] ? 0.5 * rate[format] + 0.5 * r : r;
         ++samples[format];
+        if (format == current) ++since_probe;
+        else { since_probe = 0; pending_probe = 0; }
     }
 };
 
@@ -307,6 +313,7 @@ struct tb_genus {
     cudaStream_t stream = 0;
     DevBuf<i64> d_cur, d_rep, d_disc;
     DevBuf<int> d_slots, d_lut, d_lutT;
+    DevBuf<unsigned char> d_incl;
     GenusCtx gc;
 
     // per-prime state (valid for cur_p)
@@ -319,15 +326,16 @@ struct tb_genus {
     DevBuf<int> d_tab;          // rowbase | rowfirst | rowcount   (row kernels)
     DevBuf<i64> d_nnz;          // nnz | nnzbase
     DevBuf<u64> d_lookback;     // [2^K][rows] look-back words + ticket (fused row kernel)
-    DevBuf<int> d_maxmult;      // [1] largest |entry| bound of the last T_p (narrow read-back)
+    DevBuf<int> d_maxmult;      // [2] largest |entry| bound of the last T_p (narrow read-back); rows_acc_kernel's overflow flag
     DevBuf<u32> d_rowscratch;   // row-kernel state in global memory when it does not fit shared memory
-    int *h_maxmult = nullptr;   // pinned [1]
+    int *h_maxmult = nullptr;   // pinned [2]
     struct Copier *copier = nullptr;   // background thread of the narrow read-back (started on first use)
     bool allow_narrow = true;     // TBIRCH_NO_NARROW_COPY turns the compressed read-back off
     bool force_narrow = false;    // TBIRCH_FORCE_NARROW_COPY: always the 3-byte format where it applies (no measuring)
     int64_t narrow_min_nnz = 1 << 18;   // smaller matrices are copied as they are (TBIRCH_NARROW_MIN_NNZ)
     int64_t narrow_max_ratio = 32;      // narrow row output is attempted while (p+1)/N stays below this (TBIRCH_NARROW_MAX_RATIO)
     bool allow_fused = true;
+    bool allow_acc = true;        // TBIRCH_ROWS_SORT: always the sorting row kernel (rows_kernel), never rows_acc_kernel
     bool force_checked = false;   // TBIRCH_FORCE_CHECKED: always run the checked C128 kernel in precise mode
     int last_int_mode = -1;       // tb_last_int_mode
     bool force_wide = false;      // TBIRCH_FORCE_WIDE: never run precise launches in the bounded 64-bit mode
@@ -423,7 +431,8 @@ static int upload_table(tb_genus *g, const tb_genus_desc *d)
     const size_t disc_bytes = (size_t)N * sizeof(i64);
     const size_t slot_bytes = (size_t)slots * sizeof(int);
     const size_t lut_bytes = ((size_t)N << K) * sizeof(int);
-    const size_t total = 2 * rec_bytes + disc_bytes + slot_bytes + 2 * lut_bytes;
+    const size_t incl_bytes = (size_t)(((1 << K) + 7) / 8) * N;
+    const size_t total = 2 * rec_bytes + disc_bytes + slot_bytes + 2 * lut_bytes + incl_bytes;
     if (total > g->h_table_bytes)
     {
         if (g->h_table) cudaFreeHost(g->h_table);
@@ -491,6 +500,14 @@ static int upload_table(tb_genus *g, const tb_genus_desc *d)
     int *lutT = lut + ((size_t)N << K);
     for (int k = 0; k < (1 << K); ++k)
         for (int n = 0; n < N; ++n) lutT[((size_t)n << K) + k] = d->lut[(size_t)k * N + n];
+    // which conductors see each representative, 8 per byte (rows_acc_kernel's count sweep)
+    unsigned char *incl = (unsigned char *)(lutT + ((size_t)N << K));
+    memset(incl, 0, incl_bytes);
+    for (int k = 0; k < (1 << K); ++k)
+        for (int n = 0; n < N; ++n)
+            if (d->lut[(size_t)k * N + n] != -1) incl[(size_t)(k >> 3) * N + n] |= (unsigned char)(1u << (k & 7));
+    TB_CUDA(g->d_incl.reserve(incl_bytes));
+    TB_CUDA(cudaMemcpyAsync(g->d_incl.ptr, incl, incl_bytes, cudaMemcpyHostToDevice, g->stream));
     TB_CUDA(g->d_cur.reserve((size_t)N * TB_REC_WORDS));
     TB_CUDA(g->d_rep.reserve((size_t)N * TB_REC_WORDS));
     TB_CUDA(g->d_disc.reserve(N));
@@ -550,6 +567,7 @@ extern "C" int tb_genus_create(const tb_genus_desc *d, tb_genus **out)
     g->lut.assign(d->lut, d->lut + ((size_t)g->N << g->K));
     if (int rc = upload_table(g.get(), d)) return rc;
     g->allow_fused = getenv("TBIRCH_TWO_PASS_ROWS") == nullptr;   // debugging / A-B switches
+    g->allow_acc = getenv("TBIRCH_ROWS_SORT") == nullptr;
     g->force_checked = getenv("TBIRCH_FORCE_CHECKED") != nullptr;
     g->force_wide = getenv("TBIRCH_FORCE_WIDE") != nullptr;
     g->no_fp64_reduce = getenv("TBIRCH_NO_FP64_REDUCE") != nullptr;
@@ -562,8 +580,8 @@ extern "C" int tb_genus_create(const tb_genus_desc *d, tb_genus **out)
     TB_CUDA(g->d_nnz.reserve(2 * (size_t)C));
     TB_CUDA(cudaMallocHost((void **)&g->h_err, 2 * sizeof(u64)));
     TB_CUDA(cudaMallocHost((void **)&g->h_nnz, 2 * (size_t)C * sizeof(i64)));
-    TB_CUDA(g->d_maxmult.reserve(1));
-    TB_CUDA(cudaMallocHost((void **)&g->h_maxmult, sizeof(int)));
+    TB_CUDA(g->d_maxmult.reserve(2));
+    TB_CUDA(cudaMallocHost((void **)&g->h_maxmult, 2 * sizeof(int)));
     TB_CUDA(cudaMallocHost((void **)&g->h_tab, 3 * (size_t)C * sizeof(int)));
     {
         int dev = 0;
@@ -597,6 +615,7 @@ extern "C" void tb_genus_destroy(tb_genus *g)
 {
     if (!g) return;
     g->d_cur.release(); g->d_rep.release(); g->d_disc.release(); g->d_slots.release(); g->d_lut.release(); g->d_lutT.release();
+    g->d_incl.release();
     g->d_invlut.release(); g->d_base.release(); g->d_W.release(); g->d_rp.release(); g->d_err.release();
     g->d_tab.release(); g->d_nnz.release(); g->d_lookback.release();
     for (int i = 0; i < 2; ++i) { if (g->h_stage[i]) cudaFreeHost(g->h_stage[i]); if (g->ev_stage[i]) cudaEventDestroy(g->ev_stage[i]); }
@@ -672,6 +691,18 @@ static int setup_prime(tb_genus *g, uint64_t p)
     // loop's entry guard on the coefficients (tb_neighbor.cuh); require that bound below 2^52.
     pc.fp64_reduce = ((double)p * sqrt(1125899906842624.0 / g->lambda_min) < 4503599627370496.0) ? 1u : 0u;
     if (g->no_fp64_reduce) pc.fp64_reduce = 0u;       // TBIRCH_NO_FP64_REDUCE: the literal integer loop (eisenstein_reduce)
+    {
+        // What build_neighbor hands to the reduction, bounded from the table and p (the bounds the bounded
+        // 64-bit precise mode already rests on, precise_bounds_ok64): form coefficients below 4 A (p + 4)^2,
+        // isometry entries below 2 p^2.  Below 2^50 the FP64 loop needs no per-lane magnitude test.
+        const double lp4 = log2((double)p + 4.0);
+        pc.proven_small = (pc.fp64_reduce && g->lambda_min > 0 && g->log2_coef + 2 * lp4 + 2 < 50 && 2 * lp4 + 1 < 50) ? 1u : 0u;
+        // reduced neighbor isometries: columns v with Q_rep(v) = p^2 * (a coefficient), so |entry| <= p sqrt(A / lambda_min);
+        // with the table's own isometries below 2^31 as well, the trace of cur.s * s * rep.sinv needs 32-bit factors only
+        const double iso = g->lambda_min > 0 ? 1 + log2((double)p) + 0.5 * (g->log2_coef - log2(g->lambda_min)) : 99.0;
+        pc.iso32 = (pc.proven_small && iso < 31 && g->log2_iso < 31) ? 1u : 0u;
+        if (getenv("TBIRCH_NO_PROVEN_BOUNDS")) pc.proven_small = pc.iso32 = 0u;   // A/B switch: the per-lane tests and 64-bit products
+    }
     if (pc.use_lut)
     {
         TB_CUDA(g->d_invlut.reserve(p));
@@ -859,6 +890,14 @@ static size_t rows_smem_bytes(int N, u32 P1)
     return (b + 15) & ~(size_t)15;
 }
 
+static size_t rows_acc_smem_bytes(int N, u32 P1)
+{
+    const size_t mw = (N + 31) / 32;
+    const size_t maxcols = std::min<size_t>(P1, N);
+    size_t b = (2 * mw + 2 * maxcols + 8 * 32 + 40) * 4 + maxcols;
+    return (b + 15) & ~(size_t)15;
+}
+
 extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64_t rep_begin, int64_t rep_end,
                                      tb_hecke **out)
 {
@@ -954,7 +993,9 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     R.nnzbase = d_nnz.ptr + C;
     R.nnz_out = d_nnz.ptr;
     R.maxmult = g->d_maxmult.ptr;
-    TB_CUDA(cudaMemsetAsync(g->d_maxmult.ptr, 0, sizeof(int), g->stream));
+    R.overflow = g->d_maxmult.ptr + 1;
+    R.incl = g->d_incl.ptr;
+    TB_CUDA(cudaMemsetAsync(g->d_maxmult.ptr, 0, 2 * sizeof(int), g->stream));
     size_t smem = rows_smem_bytes(N, P1);
     unsigned row_grid = (unsigned)rows;
     if (smem > 218 * 1024 || getenv("TBIRCH_ROWS_SCRATCH"))
@@ -971,10 +1012,16 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
         smem = 0;
     }
     const int threads = (int)std::min<u32>(512, std::max<u32>(64, (P1 + 31) / 32 * 32));
+    // rows_acc_kernel (accumulate with shared-memory atomics, no sort) when its state fits one SM and a class is
+    // not expected to be hit anywhere near 256 times; it reports the rare overflow and the sorting kernel redoes the pass
+    const size_t smem_acc = rows_acc_smem_bytes(N, P1);
+    bool use_acc = g->allow_acc && !R.scratch && smem_acc <= 216 * 1024 && (u64)P1 <= 48ull * (u64)N;
     static bool attrs_set = false;
     if (!attrs_set)
     {
         const int optin = 218 * 1024;   // 227 KB per CTA minus the kernels' static shared memory (8 KB parity table)
+        TB_CUDA(cudaFuncSetAttribute(rows_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+        TB_CUDA(cudaFuncSetAttribute(rows_acc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
@@ -1013,35 +1060,40 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
         TB_CUDA(cudaMemcpyAsync(d_nnz.ptr + C, g->h_nnz + C, C * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
         R.lookback = g->d_lookback.ptr;
         R.ticket = (int *)(g->d_lookback.ptr + (size_t)C * rows);
-        if (R.scratch) rows_kernel<ROWS_FUSED, true><<<row_grid, threads, 0, g->stream>>>(R);
-        else rows_kernel<ROWS_FUSED><<<row_grid, threads, smem, g->stream>>>(R);
-        ++g_launches;
-        TB_CUDA(cudaGetLastError());
-        TB_CUDA(cudaEventRecord(g->ev2, g->stream));
-        TB_CUDA(cudaMemcpyAsync(g->h_err, g->d_err.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, g->stream));
-        TB_CUDA(cudaMemcpyAsync(g->h_nnz, d_nnz.ptr, C * sizeof(i64), cudaMemcpyDeviceToHost, g->stream));
-        TB_CUDA(cudaMemcpyAsync(g->h_maxmult, g->d_maxmult.ptr, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
-        TB_CUDA(cudaStreamSynchronize(g->stream));
-        if (int rc = check_errors(g)) { return rc; }
-        for (int k = 0; k < C; ++k) h->nnz[k] = g->h_nnz[k];
-        h->maxmult = *g->h_maxmult;
-        if (!h->wide_valid && h->maxmult > 127)
+        R.extent = std::max<int64_t>(off, 1);
+        for (;;)
         {
-            // an entry does not fit 8 bits after all (few classes, large p): redo the row pass in int32
-            h->d_idx16.release(); h->d_dat8.release();
-            TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(off, 1), g->stream));
-            TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(off, 1), g->stream));
-            R.idx16 = nullptr; R.dat8 = nullptr;
-            R.data = h->d_data.ptr; R.indices = h->d_indices.ptr;
-            TB_CUDA(cudaMemsetAsync(g->d_lookback.ptr, 0, ((size_t)C * rows + 2) * sizeof(u64), g->stream));
-            if (R.scratch) rows_kernel<ROWS_FUSED, true><<<row_grid, threads, 0, g->stream>>>(R);
+            if (use_acc) rows_acc_kernel<<<(unsigned)rows, threads, smem_acc, g->stream>>>(R);
+            else if (R.scratch) rows_kernel<ROWS_FUSED, true><<<row_grid, threads, 0, g->stream>>>(R);
             else rows_kernel<ROWS_FUSED><<<row_grid, threads, smem, g->stream>>>(R);
             ++g_launches;
             TB_CUDA(cudaGetLastError());
             TB_CUDA(cudaEventRecord(g->ev2, g->stream));
+            TB_CUDA(cudaMemcpyAsync(g->h_err, g->d_err.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, g->stream));
+            TB_CUDA(cudaMemcpyAsync(g->h_nnz, d_nnz.ptr, C * sizeof(i64), cudaMemcpyDeviceToHost, g->stream));
+            TB_CUDA(cudaMemcpyAsync(g->h_maxmult, g->d_maxmult.ptr, 2 * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
             TB_CUDA(cudaStreamSynchronize(g->stream));
-            h->wide_valid = true;
+            if (int rc = check_errors(g)) { return rc; }
+            const bool redo_sort = use_acc && g->h_maxmult[1] != 0;            // a class was hit 256 times or more
+            const bool redo_wide = !h->wide_valid && (redo_sort || g->h_maxmult[0] > 127);
+            if (!redo_sort && !redo_wide) break;
+            // an entry does not fit 8 bits after all (few classes, large p): redo the row pass in int32,
+            // with the sorting kernel when the byte counters themselves overflowed
+            if (redo_sort) use_acc = false;
+            if (redo_wide)
+            {
+                h->d_idx16.release(); h->d_dat8.release();
+                TB_CUDA(h->d_data.reserve((size_t)std::max<int64_t>(off, 1), g->stream));
+                TB_CUDA(h->d_indices.reserve((size_t)std::max<int64_t>(off, 1), g->stream));
+                R.idx16 = nullptr; R.dat8 = nullptr;
+                R.data = h->d_data.ptr; R.indices = h->d_indices.ptr;
+                h->wide_valid = true;
+            }
+            TB_CUDA(cudaMemsetAsync(g->d_lookback.ptr, 0, ((size_t)C * rows + 2) * sizeof(u64), g->stream));
+            TB_CUDA(cudaMemsetAsync(g->d_maxmult.ptr, 0, 2 * sizeof(int), g->stream));
         }
+        for (int k = 0; k < C; ++k) h->nnz[k] = g->h_nnz[k];
+        h->maxmult = g->h_maxmult[0];
     }
     else
     {
@@ -1055,11 +1107,11 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
 
         TB_CUDA(cudaMemcpyAsync(g->h_err, g->d_err.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, g->stream));
         TB_CUDA(cudaMemcpyAsync(g->h_nnz, d_nnz.ptr, C * sizeof(i64), cudaMemcpyDeviceToHost, g->stream));
-        TB_CUDA(cudaMemcpyAsync(g->h_maxmult, g->d_maxmult.ptr, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+        TB_CUDA(cudaMemcpyAsync(g->h_maxmult, g->d_maxmult.ptr, 2 * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
         TB_CUDA(cudaStreamSynchronize(g->stream));
         if (int rc = check_errors(g)) { return rc; }
         for (int k = 0; k < C; ++k) h->nnz[k] = g->h_nnz[k];
-        h->maxmult = *g->h_maxmult;
+        h->maxmult = g->h_maxmult[0];
 
         int64_t total_nnz = 0;
         for (int k = 0; k < C; ++k) { h->nnzbase[k] = total_nnz; total_nnz += h->nnz[k]; }
@@ -1078,6 +1130,7 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
             R.data = h->d_data.ptr; R.indices = h->d_indices.ptr;
         }
         for (int k = 0; k < C; ++k) g->h_nnz[C + k] = h->nnzbase[k];
+        R.extent = std::max<int64_t>(total_nnz, 1);
         TB_CUDA(cudaMemcpyAsync(d_nnz.ptr + C, g->h_nnz + C, C * sizeof(i64), cudaMemcpyHostToDevice, g->stream));
         if (R.scratch) rows_kernel<ROWS_FILL, true><<<row_grid, threads, 0, g->stream>>>(R);
         else rows_kernel<ROWS_FILL><<<row_grid, threads, smem, g->stream>>>(R);
@@ -1608,7 +1661,7 @@ static int peak_one(double ops_per_iter_per_thread, double *out)
     return TB_OK;
 }
 
-extern "C" int tb_int_peak_detail(double out[5])
+extern "C" int tb_int_peak_detail(double out[7])
 {
     if (!out) return fail(TB_ERR_INVALID_ARGUMENT, "tb_int_peak_detail: null argument");
     if (int rc = require_device()) return rc;
@@ -1619,12 +1672,14 @@ extern "C" int tb_int_peak_detail(double out[5])
     if (int rc = peak_one<2>(single, &out[2])) return rc;
     if (int rc = peak_one<3>(mixed, &out[3])) return rc;
     if (int rc = peak_one<4>(mixed, &out[4])) return rc;
+    if (int rc = peak_one<5>(single, &out[5])) return rc;
+    if (int rc = peak_one<6>((double)TB_PEAK_UNROLL * TB_PEAK_OPS_TRIPLE, &out[6])) return rc;
     return TB_OK;
 }
 
 extern "C" int tb_int_peak(double *imad, double *iadd, double *mixed)
 {
-    double v[5];
+    double v[7];
     if (int rc = tb_int_peak_detail(v)) return rc;
     if (imad) *imad = v[0];
     if (iadd) *iadd = v[1];

@@ -78,3 +78,33 @@ def test_host_widening_pool_without_gpu():
         assert L.tb_host_widen_probe(entries, ctypes.byref(gbps), ctypes.byref(threads), ctypes.byref(avx2)) == 0
         assert gbps.value > 0 and threads.value >= 2 and avx2.value in (0, 1, 2)
     assert L.tb_host_widen_probe(0, None, None, None) != 0
+
+
+def test_peak_microbenchmark_counts_sass_instructions():
+    """The roofline denominator counts operations per SASS instruction: every step of int_peak_kernel is one
+    PTX instruction in an asm statement, and the unrolled loop body must hold exactly that many instructions
+    of the measured kind (16 steps x 8, 16 or 24), whatever ptxas does with them (it splits plain adds
+    between IADD3 on the alu pipe and IMAD.IADD on the fma pipe)."""
+    import collections
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("no cuobjdump")
+    sass = subprocess.run(["cuobjdump", "-sass", str(Path(__file__).resolve().parents[1] / "ternary_birch_b200" / "libtbirch.so")], capture_output=True, text=True, check=True).stdout
+    counts, name = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            counts[name] = collections.Counter()
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m and name:
+            counts[name][m.group(1)] += 1
+    want = {0: (("IMAD",), 128), 1: (("LOP3",), 128), 2: (("IADD3", "IMAD"), 128), 3: (("IADD3", "IMAD"), 256),
+            4: (("IMAD", "LOP3"), 256), 5: (("DFMA",), 128), 6: (("DFMA", "IMAD", "LOP3"), 384)}
+    for kind, (ops, n) in want.items():
+        c = next(v for k, v in counts.items() if f"int_peak_kernelILi{kind}E" in k)
+        got = sum(c[o] for o in ops)
+        assert n <= got <= n + 64, (kind, dict(c))      # the body, plus a few set-up instructions of the same kind
