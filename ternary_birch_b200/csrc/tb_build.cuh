@@ -1,6 +1,6 @@
 // tb_build.cuh -- genus construction (the caller side of the hot path).
 //
-//   quad_form_for        QuadForm<Z>::get_quad_form             QuadForm.cpp:444-777
+//   quad_form_for        the mother form of a level (same form as QuadForm<Z>::get_quad_form, QuadForm.cpp:444-777)
 //   hilbert_symbol       Math<Z>::hilbert_symbol                Math.cpp:20-57
 //   genus_mass_x24       Genus<R>::get_mass                     Genus.h:517-531
 //   proper_automorphisms QuadForm<R>::proper_automorphisms      QuadForm.h:289-528 (table: Isometry.h:359-644)
@@ -178,157 +178,168 @@ static int reduce_on_device(HostForm &q, cudaStream_t st)
     return 0;
 }
 
-// QuadForm<Z>::get_quad_form (QuadForm.cpp:444-777): a positive definite ternary form of
-// the given discriminant, ramified exactly at the flagged primes.  A quaternion-algebra
-// style search: pick b = -prod(subset of a factor base) with the prescribed Hilbert symbols
-// (a GF(2) system), start from the diagonal form <1, b, det>, strip the squares of auxiliary
-// primes from the discriminant with p^2-isotropic vectors, reduce, scale, reduce.
+// ---------------------------------------------------------------------------
+// The mother form of a level: QuadForm<Z>::get_quad_form's result (QuadForm.cpp:444-777).
+//
+// Which form comes out is part of the contract -- it is representative 0, and the order of all
+// the others follows from it -- so the construction has to make the reference's choices:
+//   1. local data: the form <1, b, c> with b = -(product of a set S of "generators") has to be
+//      ramified exactly at the flagged primes (and at the real place).  Generators are -1, 2,
+//      the primes of the discriminant and, when those do not suffice, ONE auxiliary prime
+//      (3, 5, 7, ... in turn).  Hilbert symbols are multiplicative, so S is a solution of a
+//      linear system over GF(2); the reference takes the FIRST solution in its enumeration
+//      order (subsets as binary numbers, first generator = top bit) at which the auxiliary
+//      prime stays unramified -- candidate_sets() walks the same order;
+//   2. c = radical of the discriminant with the primes of S toggled in or out; primes toggled
+//      IN (and 2) now divide the discriminant of <1, b, c> to a square too many;
+//   3. those squares are stripped: the first vector (in the order (0,0,1), (0,1,z), (1,y,z))
+//      isotropic modulo p^2 becomes a basis vector and p^2 is divided out of its row;
+//   4. reduce, scale up to the prescribed prime powers, reduce again (on the GPU:
+//      reduce_form_kernel), and check the local data of the result.
+// Written against that description; integers are __int128 (levels up to ~2^60).
+// ---------------------------------------------------------------------------
+struct LocalData {
+    std::vector<int64_t> places;     // finite places, in order: 2 first when the level is odd, then the level's primes
+    std::vector<char> ramified;      // per finite place
+    big radical = 1, disc = 1;
+
+    // bit pattern of the symbols (x, y)_v over (real place, places...), real place = top bit; 1 = symbol is -1
+    u64 pattern(big x, big y) const
+    {
+        u64 bits = (x < 0 && y < 0) ? 1u : 0u;
+        for (int64_t p : places) bits = (bits << 1) | (hilbert_symbol(x, y, p) == -1 ? 1u : 0u);
+        return bits;
+    }
+    u64 wanted() const
+    {
+        u64 bits = 1;                // definite: ramified at the real place
+        for (char r : ramified) bits = (bits << 1) | (r ? 1u : 0u);
+        return bits;
+    }
+};
+
+// Subsets of `rows` (as masks, rows[0] = top bit) whose XOR is `want`, in ascending mask order.
+template <class Visit>
+static bool candidate_sets(const std::vector<u64> &rows, u64 want, Visit visit)
+{
+    const size_t n = rows.size();
+    for (u64 pick = 1; pick < (1ull << n); ++pick)
+    {
+        u64 x = 0;
+        for (size_t j = 0; j < n; ++j)
+            if (pick & (1ull << (n - 1 - j))) x ^= rows[j];
+        if (x == want && visit(pick)) return true;
+    }
+    return false;
+}
+
+// Q(v) and the polar form B(v, e_j) = Q(v + e_j) - Q(v) - Q(e_j) of a ternary form
+static big polar_with_basis(const HostForm &q, const big v[3], int j)
+{
+    const big diag[3] = {q.a, q.b, q.c};
+    const big cross[3][3] = {{0, q.h, q.g}, {q.h, 0, q.f}, {q.g, q.f, 0}};
+    big out = 2 * diag[j] * v[j];
+    for (int i = 0; i < 3; ++i) out += cross[j][i] * v[i];
+    return out;
+}
+
+// One p^2 out of the discriminant: the first vector isotropic modulo p^2 replaces the basis vector at its
+// leading 1, whose row of the Gram matrix is then divisible by p (and its diagonal entry by p^2).
+static bool strip_square(HostForm &q, big p)
+{
+    const big pp = p * p;
+    big v[3] = {0, 0, 1};
+    int lead = 2;
+    bool found = q.c % pp == 0;
+    for (big z = 0; z < pp && !found; ++z)
+        if (q.eval(0, 1, z) % pp == 0) { v[0] = 0; v[1] = 1; v[2] = z; lead = 1; found = true; }
+    for (big y = 0; y < pp && !found; ++y)
+        for (big z = 0; z < pp && !found; ++z)
+            if (q.eval(1, y, z) % pp == 0) { v[0] = 1; v[1] = y; v[2] = z; lead = 0; found = true; }
+    if (!found) return false;
+    const big norm = q.eval(v[0], v[1], v[2]);
+    big with[3];
+    for (int j = 0; j < 3; ++j) with[j] = polar_with_basis(q, v, j);
+    // new basis: e_lead := v; only row `lead` of the Gram matrix changes
+    if (lead == 2) { q.c = norm / pp; q.f = with[1] / p; q.g = with[0] / p; }
+    else if (lead == 1) { q.b = norm / pp; q.f = with[2] / p; q.h = with[0] / p; }
+    else { q.a = norm / pp; q.g = with[2] / p; q.h = with[1] / p; }
+    return true;
+}
+
 static void quad_form_for(const std::vector<PrimeSym> &input, cudaStream_t st, int64_t out[6])
 {
-    big det = 1, disc = 1;
-    bool two_specified = false;
-    int num_ramified = 0;
+    // -- 0. what is asked for (the two argument errors are the reference's, QuadForm.cpp:456,478) --------
+    LocalData L;
+    int flagged = 0;
+    bool has_two = false;
     for (const PrimeSym &s : input)
     {
         if (s.power % 2 == 0) throw std::invalid_argument("Prime powers must be odd.");
-        if (s.p == 2) two_specified = true;
-        if (s.ramified) ++num_ramified;
-        det *= s.p;
-        for (int k = 0; k < s.power; ++k) disc *= s.p;
+        has_two |= s.p == 2;
+        flagged += s.ramified ? 1 : 0;
+        L.radical *= s.p;
+        for (int k = 0; k < s.power; ++k) L.disc *= s.p;
     }
-    if (num_ramified % 2 == 0) throw std::invalid_argument("Must specify an odd number of ramified primes.");
+    if (flagged % 2 == 0) throw std::invalid_argument("Must specify an odd number of ramified primes.");
+    if (!has_two) { L.places.push_back(2); L.ramified.push_back(0); }
+    for (const PrimeSym &s : input) { L.places.push_back(s.p); L.ramified.push_back(s.ramified ? 1 : 0); }
 
-    std::vector<PrimeSym> primes;
-    u64 target = 1;                                          // ramified at the infinite place
-    if (!two_specified) { primes.push_back(PrimeSym{2, 0, false}); target <<= 1; }
-    for (const PrimeSym &s : input) { primes.push_back(s); target <<= 1; if (s.ramified) target |= 1; }
-
-    auto sign_vector = [&](big x) {                          // QuadForm.cpp:381-390
-        u64 vec = (x == -1);
-        for (const PrimeSym &s : primes) vec = (vec << 1) | (hilbert_symbol(x, -det, s.p) == -1 ? 1u : 0u);
-        return vec;
-    };
-    auto solve = [](const std::vector<u64> &vecs, u64 start, u64 want) {   // GF2_solve_naive, 394-412
-        const u64 upper = 1ull << vecs.size();
-        for (u64 i = start + 1; i < upper; ++i)
-        {
-            u64 x = 0, mask = upper >> 1;
-            for (size_t j = 0; j < vecs.size(); ++j) { if (i & mask) x ^= vecs[j]; mask >>= 1; }
-            if (x == want) return i;
-        }
-        return (u64)0;
-    };
-
-    std::vector<big> fullbase;
-    std::vector<u64> signs;
-    fullbase.push_back(-1);
-    signs.push_back(sign_vector(-1));
-    for (const PrimeSym &s : primes) { signs.push_back(sign_vector(s.p)); fullbase.push_back(s.p); }
-
-    int64_t p = 2;
-    u64 solution = 0;
-    bool done = false, added_to_end = false;
-    while (!done)
+    // -- 1. the set S ---------------------------------------------------------------------------------------
+    std::vector<big> gens;
+    gens.push_back(-1);
+    for (int64_t p : L.places) gens.push_back(p);
+    std::vector<u64> rows;
+    for (const big &x : gens) rows.push_back(L.pattern(x, -L.radical));
+    const u64 want = L.wanted();
+    const size_t fixed = gens.size();
+    u64 chosen = 0;
+    int64_t aux = 2;
+    for (bool with_aux = false; chosen == 0; with_aux = true)
     {
-        solution = 0;
-        do
+        if (with_aux)
         {
-            solution = solve(signs, solution, target);
-            if (solution)
-            {
-                u64 mask = 1ull << fullbase.size();
-                big b = -1;
-                for (const big &q : fullbase) { mask >>= 1; if (solution & mask) b *= q; }
-                mask = 1ull << primes.size();
-                for (const PrimeSym &s : primes)
-                {
-                    mask >>= 1;
-                    const int sign = (target & mask) ? -1 : 1;
-                    if (hilbert_symbol(-b, -disc, s.p) != sign)
-                        throw std::runtime_error("Hilbert symbols do not check out. How did this happen?");
-                }
-                bool good = true;
-                for (size_t n = primes.size() + 1; n < fullbase.size(); ++n)
-                    if (hilbert_symbol(-b, -disc, (int64_t)fullbase[n]) == -1) good = false;
-                if (good) { done = true; break; }
-            }
-        } while (solution != 0);
-        if (done) break;
-        p = next_prime64(p);
-        while (disc % p == 0) p = next_prime64(p);
-        if (added_to_end) { signs.pop_back(); fullbase.pop_back(); }
-        signs.push_back(sign_vector(p));
-        fullbase.push_back(p);
-        added_to_end = true;
-    }
-
-    big b = -1;
-    u64 mask = 1ull << fullbase.size();
-    std::vector<big> base;
-    base.push_back(2);
-    for (const big &q : fullbase)
-    {
-        mask >>= 1;
-        if (solution & mask)
-        {
-            b *= q;
-            if (q > 0)
-            {
-                if (det % q == 0) det /= q;
-                else { det *= q; base.push_back(q); }
-            }
+            do { aux = next_prime64(aux); } while (L.disc % aux == 0);
+            if (aux > 100000) throw std::runtime_error("get_quad_form: no auxiliary prime found");
+            gens.resize(fixed); rows.resize(fixed);
+            gens.push_back(aux);
+            rows.push_back(L.pattern(aux, -L.radical));
         }
+        candidate_sets(rows, want, [&](u64 pick) {
+            big b = -1;
+            for (size_t j = 0; j < gens.size(); ++j)
+                if (pick & (1ull << (gens.size() - 1 - j))) b *= gens[j];
+            if (with_aux && hilbert_symbol(-b, -L.disc, aux) == -1) return false;   // the helper prime must stay unramified
+            chosen = pick;
+            return true;
+        });
     }
 
-    HostForm q{1, b, det, 0, 0, 0};
-    big N = q.disc();
-    for (const big &bp : base)                               // QuadForm.cpp:663-737
+    // -- 2. the diagonal form <1, b, c> -----------------------------------------------------------------------
+    big b = -1, c = L.radical;
+    std::vector<big> squares;                 // primes whose square has to come out of the discriminant again
+    squares.push_back(2);
+    for (size_t j = 0; j < gens.size(); ++j)
     {
-        const big pp = bp * bp;
-        while (N % pp == 0)
-        {
-            // Z_isotropic_mod_pp (QuadForm.cpp:417-442): (0,0,1), then (0,1,z), then (1,y,z)
-            big vx = 0, vy = 0, vz = 1;
-            bool found = q.eval(0, 0, 1) % pp == 0;
-            for (big z = 0; z < pp && !found; ++z)
-                if (q.eval(0, 1, z) % pp == 0) { vx = 0; vy = 1; vz = z; found = true; }
-            for (big y = 0; y < pp && !found; ++y)
-                for (big z = 0; z < pp && !found; ++z)
-                    if (q.eval(1, y, z) % pp == 0) { vx = 1; vy = y; vz = z; found = true; }
-            if (!found) break;
-            if (vx == 0 && vy == 0) { q.c /= pp; q.f /= bp; q.g /= bp; }
-            else if (vx == 0)
-            {
-                q.b += q.c * vz * vz + q.f * vz;
-                q.f += 2 * q.c * vz;
-                q.h += q.g * vz;
-                q.b /= pp; q.f /= bp; q.h /= bp;
-            }
-            else
-            {
-                q.a += q.b * vy * vy + q.c * vz * vz + q.f * vy * vz + q.g * vz + q.h * vy;
-                q.g += 2 * q.c * vz + q.f * vy;
-                q.h += 2 * q.b * vy + q.f * vz;
-                q.a /= pp; q.g /= bp; q.h /= bp;
-            }
-            N = q.disc();
-        }
+        if (!(chosen & (1ull << (gens.size() - 1 - j)))) continue;
+        b *= gens[j];
+        if (gens[j] < 0) continue;
+        if (c % gens[j] == 0) c /= gens[j];
+        else { c *= gens[j]; squares.push_back(gens[j]); }
     }
+    HostForm q{1, b, c, 0, 0, 0};
 
+    // -- 3. strip the extra squares -----------------------------------------------------------------------------
+    for (const big &p : squares)
+        while (q.disc() % (p * p) == 0 && strip_square(q, p)) {}
+
+    // -- 4. reduce, scale to the prescribed powers, reduce ---------------------------------------------------------
     if (reduce_on_device(q, st)) throw std::runtime_error("get_quad_form: intermediate form out of range");
-    for (const PrimeSym &s : primes)
+    for (const PrimeSym &s : input)
         for (int j = 3; j <= s.power; j += 2) { q.f *= s.p; q.g *= s.p; q.c *= (big)s.p * s.p; }
     if (reduce_on_device(q, st)) throw std::runtime_error("get_quad_form: intermediate form out of range");
-
-    const big x = 4 * q.a * q.b - q.h * q.h;                 // final verification, 757-771
-    mask = 1ull << primes.size();
-    for (const PrimeSym &s : primes)
-    {
-        mask >>= 1;
-        const int sign = (target & mask) ? -1 : 1;
-        if (hilbert_symbol(-x, -disc, s.p) != sign)
-            throw std::runtime_error("Hilbert symbols do not check out. How did this happen?");
-    }
+    if (L.pattern(-(4 * q.a * q.b - q.h * q.h), -L.disc) != want || q.disc() != L.disc)
+        throw std::runtime_error("get_quad_form: the constructed form does not have the requested local data");
     out[0] = (int64_t)q.a; out[1] = (int64_t)q.b; out[2] = (int64_t)q.c;
     out[3] = (int64_t)q.f; out[4] = (int64_t)q.g; out[5] = (int64_t)q.h;
 }

@@ -2,7 +2,7 @@
 (reference: src/sage/build_database.py) and the per-level JSON documents
 (reference: scripts/generate_eigenvalues.py).
 
-CPU: schema, packing, duplicate removal, job generation and the JSON layout against a stub
+CPU: schema, packing, oldform pruning, level plans and the JSON layout against a stub
 genus.  GPU: the whole batch flow on small levels, checked against FIRST-PRINCIPLES known
 answers: by modularity the rational eigenvectors at a squarefree level are the isogeny
 classes of elliptic curves of that conductor, and a_p = p + 1 - #E(F_p) is counted here
@@ -96,33 +96,39 @@ def test_database_schema_and_roundtrip(tmp_path):
         assert StubGenus.calls == [(33, [3], 77)]
         assert [v["vector"] for v in g.eigenvectors] == [[1, -2, 0], [0, 3, 1]]
         assert g.eigenvectors[0]["aps"][13] == 99 and g.eigenvectors[0]["aps"][2] == -1
-        with pytest.raises(Exception, match="No genus found"):
+        with pytest.raises(LookupError, match="is not in"):
             db.update_database_from_genus(StubGenus(35), precise=False)
     assert EigenvectorDatabase.unpack_vector(EigenvectorDatabase.pack_vector((3, -4, 0))) == [3, -4, 0]
+    # conductor 33 = 3 * 11 with the eigenvalues of the conductor-3 vector wherever both know them: an oldform pair
     assert EigenvectorDatabase.identify_duplicates(
         [dict(conductor=1, aps={2: 0}), dict(conductor=3, aps={2: 1, 5: 2}), dict(conductor=33, aps={2: 1, 7: 0}),
-         dict(conductor=33, aps={2: -1})], 11) == [2, 1]
+         dict(conductor=33, aps={2: -1})], 11) == [1, 2]
 
 
-def test_job_generation_and_json(tmp_path):
+def test_level_plans_and_json(tmp_path):
     assert [batch.sturm_bound(n) for n in (11, 13, 379, 99)] == [2, 3, 64, 24]
     assert batch.is_squarefree(30, num_primes=3) and not batch.is_squarefree(12) and not batch.is_squarefree(30, num_primes=2)
-    job = batch.generate_jobs(11 * 13, seed=3)
-    assert (job.ramified_primes, job.unramified_primes, job.ramified_primes_product) == ([11], [13], 11)
-    assert job.sturm_bound_of_ramified_primes_product == 2 and job.eigenvalues_upto == 2
-    job = batch.generate_jobs(2 * 3 * 5, seed=3, upto=5)
-    assert (job.ramified_primes, job.unramified_primes, job.eigenvalues_upto) == ([2, 3, 5], [], 5)
-    assert batch.generate_jobs(2 * 3 * 5, seed=3, upto=10 ** 6).eigenvalues_upto == batch.sturm_bound(30)
-    res = batch.find_rational_eigenvectors(batch.generate_jobs(1001, seed=9, upto=7), genus_factory=StubGenus)
-    path = tmp_path / "1001.json"
-    path.write_text(res.json())
-    doc = json.loads(path.read_text())
-    assert list(doc) == ["job", "dimensions_by_conductor", "dimension_total", "rational_eigenvectors_count",
+    assert not batch.is_squarefree(1) and batch.squarefree_primes(1001) == [7, 11, 13] and batch.squarefree_primes(49) is None
+    plan = batch.plan_level(11 * 13, seed=3)
+    assert (plan.ramified, plan.unramified, plan.ramified_product, plan.unramified_product) == ([11], [13], 11, 13)
+    assert plan.sturm == 2 and plan.upto == 2
+    plan = batch.plan_level(2 * 3 * 5, seed=3, upto=5)
+    assert (plan.ramified, plan.unramified, plan.upto) == ([2, 3, 5], [], 5)
+    assert batch.plan_level(2 * 3 * 5, seed=3, upto=10 ** 6).upto == batch.sturm_bound(30)
+    with pytest.raises(ValueError):
+        batch.plan_level(12, seed=1)
+    doc = batch.run_level(batch.plan_level(1001, seed=9, upto=7), genus_factory=StubGenus)
+    path = batch.write_document(doc, tmp_path)
+    assert path.endswith("1001.json")
+    raw = json.loads(open(path).read())
+    # the reference's document: same keys, same order (scripts/generate_eigenvalues.py:22-47)
+    assert list(raw) == ["job", "dimensions_by_conductor", "dimension_total", "rational_eigenvectors_count",
                          "rational_eigenvectors"]
-    assert list(doc["job"])[:8] == ["level", "seed", "ramified_primes", "ramified_primes_product", "unramified_primes",
-                                    "unramified_primes_product", "sturm_bound_of_ramified_primes_product",
-                                    "eigenvalues_upto"]
-    assert doc["job"]["elapsed_seconds"] >= doc["job"]["elapsed_seconds_eigenvalues"] >= 0
+    assert list(raw["job"]) == ["level", "seed", "ramified_primes", "ramified_primes_product", "unramified_primes",
+                                "unramified_primes_product", "sturm_bound_of_ramified_primes_product",
+                                "eigenvalues_upto", "elapsed_seconds", "elapsed_seconds_genus",
+                                "elapsed_seconds_eigenvectors", "elapsed_seconds_eigenvalues"]
+    assert raw["job"]["elapsed_seconds"] >= raw["job"]["elapsed_seconds_eigenvalues"] >= 0
     back = batch.load_result(path)
     assert back["dimensions_by_conductor"] == {1: 3, 1001: 2} and back["rational_eigenvectors_count"] == 2
     assert back["rational_eigenvectors"][0] == dict(vector=[1, -2, 0], aps={2: -1, 3: -3, 5: -5}, conductor=1)
@@ -169,10 +175,10 @@ def test_batch_flow_against_elliptic_curves(tmp_path):
         again = db.get_genus_with_eigenvectors(37, precise=False)
         assert sorted(v["aps"][2] for v in again.eigenvectors) == [-2, 0]
         assert again.compute_eigenvalues(41, precise=True) is not None
-    res = batch.find_rational_eigenvectors(batch.generate_jobs(37, seed=1))
-    assert res.rational_eigenvectors_count == 2 and res.dimension_total == sum(res.dimensions_by_conductor.values())
-    assert res.job.eigenvalues_upto == batch.sturm_bound(37) == 7
-    assert sorted(v["aps"][7] for v in res.rational_eigenvectors) == [-1, -1]
+    doc = batch.run_level(batch.plan_level(37, seed=1))
+    assert doc["rational_eigenvectors_count"] == 2 and doc["dimension_total"] == sum(doc["dimensions_by_conductor"].values())
+    assert doc["job"]["eigenvalues_upto"] == batch.sturm_bound(37) == 7
+    assert sorted(v["aps"][7] for v in doc["rational_eigenvectors"]) == [-1, -1]
 
 
 # Number of isogeny classes of elliptic curves of each squarefree conductor 11 <= N <= 130 (Cremona's tables):
