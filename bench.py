@@ -125,7 +125,13 @@ def reference_sample(primes, precise=False, timeout=1200):
         total, slowest = 0, 0.0
         for pr in procs:
             out, _ = pr.communicate(timeout=timeout)
-            rec = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+            lines = [l for l in out.splitlines() if l.startswith("{")]
+            rec = json.loads(lines[-1]) if lines else {"error": "no output", "what": f"exit code {pr.returncode}"}
+            if "neighbors" not in rec:
+                for other in procs:
+                    if other.poll() is None:
+                        other.kill()
+                raise RuntimeError(f"reference binary failed: {rec}")
             total += rec["neighbors"]
             slowest = max(slowest, rec["seconds"])
         return total, slowest, kind

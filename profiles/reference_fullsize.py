@@ -18,8 +18,18 @@ cores = os.cpu_count() or 1
 avail_gb = next(int(l.split()[1]) for l in open("/proc/meminfo") if l.startswith("MemAvailable")) / 1e6
 n = max(1, min(cores, 16, int(avail_gb // 12)))
 big = [9973, 9967, 9949, 9941, 9931, 9929, 9923, 9907, 9901, 9887, 9883, 9871, 9859, 9857, 9851, 9839][:n]
-t0 = time.time()
-neighbors, slowest, kind = bench.reference_sample(big, timeout=3000)
+notes = []
+while True:
+    t0 = time.time()
+    try:
+        neighbors, slowest, kind = bench.reference_sample(big, timeout=3000)
+        break
+    except RuntimeError as e:      # e.g. std::bad_alloc with too many 10 GB processes at once: halve and retry
+        notes.append(f"{n} processes: {e}")
+        if n == 1:
+            raise
+        n //= 2
+        big = big[:n]
 wall = time.time() - t0
 small = bench.REF_SAMPLE_PRIMES[:n]
 n2, s2, _ = bench.reference_sample(small)
@@ -31,5 +41,7 @@ rec = dict(kind=kind, cores_used=n, host_cores=cores,
            neighbors_per_s_per_core=neighbors / slowest / n,
            what=f"unmodified reference, {n} processes x one prime each of {big[0]}..{big[-1]}, int64, "
                 f"{slowest:.1f} s for the slowest call")
+if notes:
+    rec["retries"] = notes
 rec["sampled_over_full"] = rec["sampled"]["neighbors_per_s_per_core"] / rec["full"]["neighbors_per_s_per_core"]
 print(json.dumps(rec))

@@ -108,10 +108,13 @@ __global__ void la_from_csr_kernel(LaCtx c, const int *data, const int *indices,
 }
 __global__ void la_from_dense_kernel(LaCtx c, const i64 *src)
 {
-    const int row = blockIdx.y;
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= c.cols) return;
-    c.M[(size_t)row * c.ld + col] = la_to_mont(src[(size_t)row * c.cols + col], c);
+    // grid-stride over all cells: no limit on the number of rows
+    const size_t cells = (size_t)c.rows * c.cols, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += stride)
+    {
+        const size_t row = i / c.cols, col = i - row * c.cols;
+        c.M[row * c.ld + col] = la_to_mont(src[i], c);
+    }
 }
 
 // Cooperative grid; global warp gw handles rows gw, gw + GW, ...; lane = column inside the

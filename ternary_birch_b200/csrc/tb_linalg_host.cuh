@@ -30,16 +30,18 @@ struct LaBuf {
 
 static void la_keep_pool()
 {
-    static bool done = false;
-    if (done) return;
+    static std::atomic<uint64_t> done_mask(0);          // per device: a process may drive several GPUs
     int dev = 0;
     cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done_mask.load() & bit) return;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
     {
         uint64_t keep = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    done = true;
+    done_mask.fetch_or(bit);
 }
 
 static bool la_is_prime(uint32_t n)
@@ -206,9 +208,8 @@ extern "C" int tb_modkernel_dense(const int64_t *Msrc, int64_t rows, int64_t col
         LaBuf<i64> src;
         TB_CUDA(src.alloc((size_t)rows * cols, false));
         TB_CUDA(cudaMemcpy(src.ptr, Msrc, (size_t)rows * cols * sizeof(i64), cudaMemcpyHostToDevice));
-        if (rows > 65535) return fail(TB_ERR_INVALID_ARGUMENT, "tb_modkernel_dense: more than 65535 rows");
-        const dim3 grid((unsigned)((cols + 127) / 128), (unsigned)rows);
-        la_from_dense_kernel<<<grid, 128>>>(c, src.ptr);
+        const size_t cells = (size_t)rows * cols;
+        la_from_dense_kernel<<<(unsigned)std::min<size_t>((cells + 255) / 256, 148 * 32), 256>>>(c, src.ptr);
         ++g_launches;
         TB_CUDA(cudaGetLastError());
         TB_CUDA(cudaDeviceSynchronize());

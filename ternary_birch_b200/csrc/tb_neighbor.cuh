@@ -803,8 +803,13 @@ __device__ __forceinline__ int reduce_loop_fp64(DReduce &d)
 // hot path only asks whether the form lies on a boundary of the reduction domain at all
 // (on_boundary), which is the first clause of each of the ten fix-ups -- when none holds for the
 // form as the loop left it, none of them fires and nothing changes.
+#ifdef TB_BOUNDARY_INLINE      /* A/B timing: the fix-ups inlined into the hot path, as in round 1 */
+#define TB_BOUNDARY_ATTR __forceinline__
+#else
+#define TB_BOUNDARY_ATTR __noinline__
+#endif
 template <class Z>
-__device__ __noinline__ void reduce_boundary(Form<Z> &q, Iso<Z> &s)
+__device__ TB_BOUNDARY_ATTR void reduce_boundary(Form<Z> &q, Iso<Z> &s)
 {
     Z a = q.a, b = q.b, c = q.c, f = q.f, g = q.g, h = q.h, t;
     const Z zero = Z(0);
@@ -875,6 +880,9 @@ __device__ __forceinline__ bool reduce_neighbor(Form<Z> &q, Iso<Z> &s, bool fp64
     s.a11 = Z(__double2ll_rn(d.s11)); s.a12 = Z(__double2ll_rn(d.s12)); s.a13 = Z(__double2ll_rn(d.s13));
     s.a21 = Z(__double2ll_rn(d.s21)); s.a22 = Z(__double2ll_rn(d.s22)); s.a23 = Z(__double2ll_rn(d.s23));
     s.a31 = Z(__double2ll_rn(d.s31)); s.a32 = Z(__double2ll_rn(d.s32)); s.a33 = Z(__double2ll_rn(d.s33));
+#ifdef TB_BOUNDARY_INLINE
+    reduce_boundary(q, s);
+#else
     if (on_boundary)
     {
         Form<Z> tq = q;          // copies: only these are address-taken by the out-of-line call
@@ -883,6 +891,7 @@ __device__ __forceinline__ bool reduce_neighbor(Form<Z> &q, Iso<Z> &s, bool fp64
         q = tq;
         s = ts;
     }
+#endif
     return iters <= TB_REDUCE_CAP;
 }
 

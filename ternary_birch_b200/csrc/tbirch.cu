@@ -1016,8 +1016,11 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     // not expected to be hit anywhere near 256 times; it reports the rare overflow and the sorting kernel redoes the pass
     const size_t smem_acc = rows_acc_smem_bytes(N, P1);
     bool use_acc = g->allow_acc && !R.scratch && smem_acc <= 216 * 1024 && (u64)P1 <= 48ull * (u64)N;
-    static bool attrs_set = false;
-    if (!attrs_set)
+    // function attributes are per device (context): set them once on each device this process uses
+    static std::atomic<uint64_t> attrs_mask(0);
+    int attr_dev = 0;
+    TB_CUDA(cudaGetDevice(&attr_dev));
+    if (!(attrs_mask.load() & (1ull << (attr_dev & 63))))
     {
         const int optin = 218 * 1024;   // 227 KB per CTA minus the kernels' static shared memory (8 KB parity table)
         TB_CUDA(cudaFuncSetAttribute(rows_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
@@ -1028,7 +1031,7 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
         TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_COUNT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_FILL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_FUSED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attrs_set = true;
+        attrs_mask.fetch_or(1ull << (attr_dev & 63));
     }
 
     TB_CUDA(cudaEventRecord(g->ev0, g->stream));
@@ -1250,6 +1253,7 @@ extern "C" int tb_eigenvalues(tb_genus *g, uint64_t p, int precise, int64_t V, c
     for (int64_t v = 0; v < V; ++v) reps.push_back((int)rep_index[v]);
     std::sort(reps.begin(), reps.end());
     reps.erase(std::unique(reps.begin(), reps.end()), reps.end());
+    if (reps.size() > 65535) return fail(TB_ERR_INVALID_ARGUMENT, "tb_eigenvalues: more than 65535 distinct representatives");
     std::vector<uint32_t> base;
     base_points_for(g, p, reps, base);
 
