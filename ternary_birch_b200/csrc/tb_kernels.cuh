@@ -179,6 +179,7 @@ struct NbrLaunch {
     u32 pad;
     u64 total;        // rows * P1
     InvDiv dP1;
+    u64 mP1;          // floor(2^64 / P1) + 1 when total < 2^32 (two 32-bit multiplies give i / P1 exactly), else 0
     const RepPrime *rp;
     u32 *W;
     i64 *records;
@@ -206,9 +207,23 @@ neighbors_kernel(const __grid_constant__ GenusCtx gc, const __grid_constant__ Pr
     const bool live = i_raw < L.total;
     const u64 i = live ? i_raw : L.total - 1;
     {
-        u64 t64;
-        const u64 row = udivmod(i, L.dP1, t64);
-        const u32 t = (u32)t64;
+        // (row, t) = divmod(i, p + 1).  Below 2^32 neighbors: i * M >> 64 with M = floor(2^64 / P1) + 1 is exact
+        // (error i (M P1 - 2^64) / (P1 2^64) < 2^-32 < 1 / P1)
+        u64 row;
+        u32 t;
+        if (L.mP1)
+        {
+            const u32 i32 = (u32)i;
+            const u64 mid = (u64)i32 * (u32)(L.mP1 >> 32) + (((u64)i32 * (u32)L.mP1) >> 32);
+            row = mid >> 32;
+            t = i32 - (u32)row * L.P1;
+        }
+        else
+        {
+            u64 t64;
+            row = udivmod(i, L.dP1, t64);
+            t = (u32)t64;
+        }
         const int n = L.rep_list ? L.rep_list[row] : L.rep_begin + (int)row;
         const RepPrime rp = L.rp[row];
 

@@ -43,8 +43,8 @@ struct PrimeCtx {
     u32 m32;          // floor(2^32 / p) when p < 2^16 (32-bit Barrett), else 0
     u32 narrow_trace; // two-limb modes: composed isometry / denominator proven below 2^61 (64-bit trace)
     u32 proven_small; // every value build_neighbor hands to the reduction is proven below 2^50 (no per-lane test)
-    u32 iso32;        // 64-bit modes: table isometries and reduced neighbor isometries proven below 2^31 (32-bit products)
-    u32 pad3;
+    u32 iso32;        // table isometries and reduced neighbor isometries proven below 2^31 (32-bit products, int32 reduce isometry)
+    u32 f32_tail;     // fp64_reduce and small table forms (c < 2^24, b < 2^20): the reduce loop finishes in binary32
     u64 pp;
     InvDiv dp;        // division by p
     InvDiv dpp;       // division by p^2
@@ -175,6 +175,15 @@ struct Iso {
 // ---------------------------------------------------------------------------
 // Fp on canonical residues, p < 2^31.
 // ---------------------------------------------------------------------------
+// The general paths (p >= 2^16: 64-bit product and 2-by-1 division; p >= 2^22 or no table: Fermat
+// inverse) live out of line: inlined they put ~50 resp. ~110 cold instructions after every hot
+// multiplication / inversion, and the kernel is bound by instruction fetch.
+__device__ __noinline__ u32 fp_mul_wide(u32 a, u32 b, const PrimeCtx &pc)
+{
+    u64 r;
+    udivmod((u64)a * (u64)b, pc.dp, r);
+    return (u32)r;
+}
 __device__ __forceinline__ u32 fp_mul(u32 a, u32 b, const PrimeCtx &pc)
 {
     if (pc.m32)
@@ -184,9 +193,7 @@ __device__ __forceinline__ u32 fp_mul(u32 a, u32 b, const PrimeCtx &pc)
         u32 r = x - __umulhi(x, pc.m32) * pc.p;
         return r >= pc.p ? r - pc.p : r;
     }
-    u64 r;
-    udivmod((u64)a * (u64)b, pc.dp, r);
-    return (u32)r;
+    return fp_mul_wide(a, b, pc);
 }
 __device__ __forceinline__ u32 fp_add(u32 a, u32 b, u32 p) { u32 s = a + b; return s >= p ? s - p : s; }
 __device__ __forceinline__ u32 fp_sub(u32 a, u32 b, u32 p) { return a >= b ? a - b : a + p - b; }
@@ -203,11 +210,15 @@ __device__ __forceinline__ u32 fp_pow(u32 a, u32 e, const PrimeCtx &pc)
 }
 // Fp::inverse (Fp.h:147-150): table below 2^22 (built per prime by
 // inverse_lut_kernel), Fermat above.  F2::inverse for p = 2.
-__device__ __forceinline__ u32 fp_inv(u32 a, const PrimeCtx &pc)
+__device__ __noinline__ u32 fp_inv_general(u32 a, const PrimeCtx &pc)
 {
     if (pc.p == 2u) return a & 1u;
-    if (pc.use_lut) return __ldg(pc.inv_lut + a);
     return a ? fp_pow(a, pc.p - 2u, pc) : 0u;
+}
+__device__ __forceinline__ u32 fp_inv(u32 a, const PrimeCtx &pc)
+{
+    if (pc.use_lut) return __ldg(pc.inv_lut + a);      // use_lut implies p > 2
+    return fp_inv_general(a, pc);
 }
 // Fp::mod of a signed 64-bit coefficient (Fp.h:29-35).
 __device__ __forceinline__ u32 fp_mod_i64(i64 x, const PrimeCtx &pc)
@@ -583,35 +594,12 @@ __device__ __noinline__ bool eisenstein_reduce(Form<Z> &q, Iso<Z> &s)
 // 1 / d to ~2^-36 relative: the hardware's ~20-bit seed and ONE Newton step.  That is all the shear
 // quotients need: on a positive definite form |h| < 2 sqrt(ab), |f| < 2 sqrt(bc), |g| < 2 sqrt(ac), so
 // with coefficients below 2^50 every quotient (a-h)/2a, (b-f)/2b, (a-g)/2a is below 2^26 in magnitude
-// and its estimate is within 2^-10 of the true value -- dshear_t's exact remainder then decides
-// between floor and floor + 1.  (TB_RCP_STEPS=2 restores the second step for A/B timing.)
-#ifndef TB_RCP_STEPS
-#define TB_RCP_STEPS 1
-#endif
-__device__ __forceinline__ double rcp_f64(double d)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    double e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-#if TB_RCP_STEPS > 1
-    e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-#endif
-    return r;
-}
+// and its estimate is within 2^-10 of the true value -- shear_quot's exact remainder then decides
+// between floor and floor + 1.
 // x with its sign bit XORed by m (m = 0 or 0x80000000): one LOP3
 __device__ __forceinline__ double xflip(double x, u32 m)
 {
     return __hiloint2double(__double2hiint(x) ^ (int)m, __double2loint(x));
-}
-__device__ __forceinline__ double dflip(double x, bool neg) { return xflip(x, neg ? 0x80000000u : 0u); }
-// conditional swap, select form (ALU pipe: 4 FSEL)
-__device__ __forceinline__ void dswap_sel(bool p, double &x, double &y)
-{
-    const double t = p ? y : x;
-    y = p ? x : y;
-    x = t;
 }
 // conditional swap, arithmetic form (FP64 pipe: DADD + 2 DFMA), m = 1.0 to swap, 0.0 to keep;
 // exact for integer-valued operands with |y - x| < 2^53
@@ -625,17 +613,7 @@ __device__ __forceinline__ void dswap_fma(double m, double &x, double &y)
 //     t = a >= h ? (a-h) div 2a : -((a+h-1) div 2a)
 // is floor((a-h)/2a) in both branches (for h > a: -ceil((h-a)/2a) = -floor((h-a+2a-1)/2a)).
 // q = RN(num * rden) by the 1.5*2^52 trick is floor or floor+1 (the estimate is within 1/2 of
-// num/den for |num/den| < 2^49); the exact remainder tells which.  `act` = 1.0 or 0.0 freezes
-// finished lanes.
-__device__ __forceinline__ double dshear_t(double a, double h, double den, double rden, double act)
-{
-    const double num = a - h;
-    const double magic = 6755399441055744.0;   // 1.5 * 2^52
-    const double q = __dadd_rn(__fma_rn(num, rden, magic), -magic);
-    const double r = __fma_rn(-q, den, num);    // exact
-    const double corr = __hiloint2double(r < 0.0 ? (int)0xBFF00000 : 0, 0);   // -1.0 or 0.0
-    return (q + corr) * act;
-}
+// num/den for |num/den| < 2^49); the exact remainder tells which (shear_quot below).
 
 // 2^50 magnitude test on an int64
 __device__ __forceinline__ bool small50(i64 v) { return (u64)(v + (1ll << 50)) < (1ull << 51); }
@@ -644,172 +622,269 @@ __device__ __forceinline__ bool fits50(I64T<TAG> x) { return small50(x.v); }
 template <bool CHK>
 __device__ __forceinline__ bool fits50(I128<CHK> x) { return x.fits_i64() && small50((i64)x.lo); }
 
+
+// Real-type helpers of the loop body: the form part of a trip runs in binary64 or, once every value
+// is a small integer, in binary32 (reduce_loop_fp64's tail); the isometry stays binary64 throughout.
+__device__ __forceinline__ double rmagic(double) { return 6755399441055744.0; }   // 1.5 * 2^52
+__device__ __forceinline__ float rmagic(float) { return 12582912.0f; }            // 1.5 * 2^23
+__device__ __forceinline__ double rcp_seeded(double d, bool on)
+{
+    // hardware seed with a finished lane's zeroed, one Newton step (0 stays 0 through the Newton step)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = __hiloint2double(on ? __double2hiint(r) : 0, 0);
+    const double e = fma(-d, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ float rcp_seeded(float d, bool on)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return on ? r : 0.0f;
+}
+__device__ __forceinline__ double radd(double x, double y) { return __dadd_rn(x, y); }
+__device__ __forceinline__ float radd(float x, float y) { return __fadd_rn(x, y); }
+__device__ __forceinline__ double rfma(double x, double y, double z) { return __fma_rn(x, y, z); }
+__device__ __forceinline__ float rfma(float x, float y, float z) { return __fmaf_rn(x, y, z); }
+__device__ __forceinline__ int rsign(double r) { return __double2hiint(r) >> 31; }    // -1 if r < 0 (r is never -0)
+__device__ __forceinline__ int rsign(float r) { return __float_as_int(r) >> 31; }
+__device__ __forceinline__ int rquot(double qm) { return __double2loint(qm); }        // int32(qm - magic)
+__device__ __forceinline__ int rquot(float qm) { return __float_as_int(qm) - 0x4B400000; }
+__device__ __forceinline__ double rcorr(double, int m) { return __hiloint2double(m & (int)0xBFF00000, 0); }   // -1.0 or 0.0
+__device__ __forceinline__ float rcorr(float, int m) { return __int_as_float(m & (int)0xBF800000); }
+__device__ __forceinline__ double rflip(double x, u32 m) { return xflip(x, m); }
+__device__ __forceinline__ float rflip(float x, u32 m) { return __int_as_float(__float_as_int(x) ^ (int)m); }
+__device__ __forceinline__ double rabs(double x) { return fabs(x); }
+__device__ __forceinline__ float rabs(float x) { return fabsf(x); }
+__device__ __forceinline__ double rwide(double t) { return t; }
+__device__ __forceinline__ double rwide(float t) { return (double)t; }
+
+// floor((x - y) / den), see above; a finished lane has rden = 0, hence quotient 0 (its remainder
+// x - y is a - h, b - f or a - g of a form that passed the exit test: never negative)
+template <class F>
+__device__ __forceinline__ F shear_quot(F x, F y, F den, F rden)
+{
+    const F num = x - y;
+    const F q = radd(rfma(num, rden, rmagic(F(0))), -rmagic(F(0)));
+    const F r = rfma(-q, den, num);            // exact
+    return q + rcorr(F(0), rsign(r));          // q - 1 if r < 0 (sign mask of r ANDed into the bits of -1.0)
+}
+template <class F>
+__device__ __forceinline__ void rswap(bool p, F &x, F &y)
+{
+    const F t = p ? y : x;
+    y = p ? x : y;
+    x = t;
+}
+
+// Isometry of the loop: binary64 entries with lazy column signs (actual column i = stored column i
+// with its sign bit XOR sg_i).  The shears only ever need the pairwise products of the signs, so
+// those are what is carried -- x12 = sg1^sg2, x23 = sg2^sg3, x13 = sg1^sg3, sign-bit masks -- next
+// to sg1 itself; sg2 = sg1^x12 and sg3 = sg1^x13 are rebuilt once at the end.  A swap-and-negate
+// of two columns permutes the pairwise masks (the common negation cancels in them):
+//   (c1,c2,c3) <- (-c2,-c1,-c3):  x12 stays, x23 <-> x13, sg1 <- sg2 ^ S = sg1 ^ x12 ^ S
+//   (c1,c2,c3) <- (-c1,-c3,-c2):  x23 stays, x12 <-> x13, sg1 <- sg1 ^ S
+struct DIso {
+    double s11, s12, s13, s21, s22, s23, s31, s32, s33;
+    u32 sg1, x12, x23, x13;
+};
+
+// One trip on every lane of the warp; finished lanes are frozen: their reciprocals (hence shear
+// quotients) and swap predicates are masked, the fix step and the sign normalisation cannot fire on
+// them (exit test: sum >= 0; normalisation is idempotent).
+template <class F>
+__device__ __forceinline__ void reduce_trip(F &a, F &b, F &c, F &f, F &g, F &h, F &sum, DIso &S, bool &active)
+{
+    const F zero = F(0), one = F(1);
+    const u32 SIGN = 0x80000000u;
+    // a + b + f + g + h < 0                                          542-549
+    // (some lane of nearly every trip needs it, so it runs unconditionally with a 0/1 multiplier
+    //  instead of under a vote and a divergent branch)
+    {
+        const bool fix = sum < zero;
+        const F fm = fix ? one : zero;
+        const double fd = fix ? 1.0 : 0.0;
+        const double m13 = xflip(fd, S.x13), m23 = xflip(fd, S.x23);
+        S.s13 = fma(m23, S.s12, fma(m13, S.s11, S.s13));
+        S.s23 = fma(m23, S.s22, fma(m13, S.s21, S.s23));
+        S.s33 = fma(m23, S.s32, fma(m13, S.s31, S.s33));
+        c = rfma(fm, sum, c);
+        f = rfma(fm, h + (b + b), f);
+        g = rfma(fm, h + (a + a), g);
+    }
+    // shear 1: col2 += t col1                                        551-567
+    const F den = a + a;
+    const F rden = rcp_seeded(den, active);
+    {
+        const F t = shear_quot(a, h, den, rden);
+        const double ts = xflip(rwide(t), S.x12);
+        S.s12 = fma(ts, S.s11, S.s12); S.s22 = fma(ts, S.s21, S.s22); S.s32 = fma(ts, S.s31, S.s32);
+        const F temp = a * t;
+        h += temp;
+        b = rfma(h, t, b);
+        f = rfma(g, t, f);
+        h += temp;
+    }
+    // shear 2: col3 += t col2                                        569-585
+    {
+        const F den2 = b + b;
+        const F rden2 = rcp_seeded(den2, active);
+        const F t = shear_quot(b, f, den2, rden2);
+        const double ts = xflip(rwide(t), S.x23);
+        S.s13 = fma(ts, S.s12, S.s13); S.s23 = fma(ts, S.s22, S.s23); S.s33 = fma(ts, S.s32, S.s33);
+        const F temp = b * t;
+        f += temp;
+        c = rfma(f, t, c);
+        g = rfma(h, t, g);
+        f += temp;
+    }
+    // shear 3: col3 += t col1 (a, hence 2a, is unchanged)             587-603
+    {
+        const F t = shear_quot(a, g, den, rden);
+        const double ts = xflip(rwide(t), S.x13);
+        S.s13 = fma(ts, S.s11, S.s13); S.s23 = fma(ts, S.s21, S.s23); S.s33 = fma(ts, S.s31, S.s33);
+        const F temp = a * t;
+        g += temp;
+        c = rfma(g, t, c);
+        f = rfma(h, t, f);
+        g += temp;
+    }
+    // sort a <= b <= c with the reference's tie-breaks                605-624
+    // (form pairs swap by select on the ALU pipe, isometry columns arithmetically on the FP64 pipe)
+    {
+        const bool p = active & ((a > b) | ((a == b) & (rabs(f) > rabs(g))));
+        const double m = p ? 1.0 : 0.0;
+        rswap(p, a, b); rswap(p, f, g);
+        dswap_fma(m, S.s11, S.s12); dswap_fma(m, S.s21, S.s22); dswap_fma(m, S.s31, S.s32);
+        const u32 o23 = S.x23;                         // (c1,c2,c3) <- (-c2,-c1,-c3)
+        S.sg1 ^= p ? (S.x12 ^ SIGN) : 0u; S.x23 = p ? S.x13 : S.x23; S.x13 = p ? o23 : S.x13;
+    }
+    {
+        const bool p = active & ((b > c) | ((b == c) & (rabs(g) > rabs(h))));
+        const double m = p ? 1.0 : 0.0;
+        rswap(p, b, c); rswap(p, g, h);
+        dswap_fma(m, S.s12, S.s13); dswap_fma(m, S.s22, S.s23); dswap_fma(m, S.s32, S.s33);
+        const u32 o12 = S.x12;                         // (c1,c2,c3) <- (-c1,-c3,-c2)
+        S.sg1 ^= p ? SIGN : 0u; S.x12 = p ? S.x13 : S.x12; S.x13 = p ? o12 : S.x13;
+    }
+    {
+        const bool p = active & ((a > b) | ((a == b) & (rabs(f) > rabs(g))));
+        const double m = p ? 1.0 : 0.0;
+        rswap(p, a, b); rswap(p, f, g);
+        dswap_fma(m, S.s11, S.s12); dswap_fma(m, S.s21, S.s22); dswap_fma(m, S.s31, S.s32);
+        const u32 o23 = S.x23;
+        S.sg1 ^= p ? (S.x12 ^ SIGN) : 0u; S.x23 = p ? S.x13 : S.x23; S.x13 = p ? o23 : S.x13;
+    }
+    // sign normalisation                                              626-687
+    // Restated: if f g h > 0 (all nonzero, evenly many negative) flip the negative ones;
+    // otherwise flip the positive ones and, when that is an odd number of flips, also the
+    // first zero among f, g, h (column flips must come in pairs: det stays +p^2).
+    {
+        const bool fneg = f < zero, gneg = g < zero, hneg = h < zero;
+        const bool fpos = f > zero, gpos = g > zero, hpos = h > zero;
+        const bool caseA = (f * g) * h > zero;
+        const bool oddB = !caseA & ((fpos != gpos) != hpos);
+        const bool fz = !fneg & !fpos, gz = !gneg & !gpos, hz = !hneg & !hpos;
+        const bool f1 = (caseA ? fneg : fpos) | (oddB & fz);
+        const bool f2 = (caseA ? gneg : gpos) | (oddB & !fz & gz);
+        const bool f3 = (caseA ? hneg : hpos) | (oddB & !fz & !gz & hz);
+        const u32 n1 = f1 ? SIGN : 0u, n2 = f2 ? SIGN : 0u, n3 = f3 ? SIGN : 0u;
+        f = rflip(f, n1); g = rflip(g, n2); h = rflip(h, n3);
+        S.sg1 ^= n1; S.x12 ^= n1 ^ n2; S.x23 ^= n2 ^ n3; S.x13 ^= n1 ^ n3;
+    }
+    // exit test                                                       689-690
+    sum = (((a + b) + f) + g) + h;
+    const bool done = (rabs(f) <= b) & (rabs(g) <= a) & (rabs(h) <= a) & (sum >= zero);
+    active = active & !done;
+}
+
+// Does any post-loop fix-up of QuadForm.h:693-764 fire on the form as the loop left it?  The ten
+// fix-ups run in sequence, each on the state its predecessors left; when none of their conditions
+// holds on the initial state, the first changes nothing, so the second sees the same state, and so
+// on: nothing fires (759 repeats 744).  Exact in binary64 and, in the tail, in binary32 (every
+// operand is an integer below 2^23).
+template <class F>
+__device__ __forceinline__ bool boundary_fixup_fires(F a, F b, F c, F f, F g, F h)
+{
+    const F zero = F(0);
+    const F sum = (((a + b) + f) + g) + h;
+    return ((sum == zero) & ((a + a) + (g + g) + h > zero)) |      // 693
+           ((a == -h) & (g != zero)) |                             // 702
+           ((a == -g) & (h != zero)) |                             // 710
+           ((b == -f) & (h != zero)) |                             // 718
+           ((a == h) & (g > f + f)) |                              // 726
+           ((a == g) & (h > f + f)) |                              // 732
+           ((b == f) & (h > g + g)) |                              // 738
+           ((a == b) & (rabs(f) > rabs(g))) |                      // 744, 759
+           ((b == c) & (rabs(g) > rabs(h)));                       // 752
+}
+
+// Binary32 tail (f32_tail).  Diagonal coefficients never grow and after a trip's sort c is the
+// largest; |f|, |g|, |h| < 2 c, the running sum < 8 c, shear intermediates (a t, h + a t) < 4.5 c.
+// Once every unfinished lane of the warp has c < 2^20 -- after ~5 of the ~12.6 trips a warp makes
+// at p ~ 10^4 -- every value of every later trip is an integer below 2^23 and binary32
+// FFMA/FADD/FMUL are exact on it (one rounding per operation, of an integer below 2^24).  The
+// quotient estimate num * rcp(den) is within 2^-10 of num / den (|num / den| < 2^12), so RN gives
+// floor or floor + 1 and the exact remainder decides, as in binary64.  Finished lanes hold reduced
+// forms and are carried along with zero quotients: the host requires c < 2^24 and b < 2^20 on
+// every table form (their running sum is at most 5 b), so their values convert exactly as well.
+//
+// Returns the trip count; on_boundary says whether some fix-up of QuadForm.h:693-764 fires.
 struct DReduce {
     double a, b, c, f, g, h;
     double s11, s12, s13, s21, s22, s23, s31, s32, s33;
+    bool on_boundary;
 };
 
-// Returns the trip count; the caller converts the state back and runs the
-// (rare, branchy) boundary fix-ups in integer arithmetic.
-__device__ __forceinline__ int reduce_loop_fp64(DReduce &d)
+__device__ __forceinline__ int reduce_loop_fp64(DReduce &d, bool f32_tail)
 {
-    double a = d.a, b = d.b, c = d.c, f = d.f, g = d.g, h = d.h;
-    double s11 = d.s11, s12 = d.s12, s13 = d.s13, s21 = d.s21, s22 = d.s22, s23 = d.s23;
-    double s31 = d.s31, s32 = d.s32, s33 = d.s33;
-    // lazy column signs as sign-bit masks: actual column i = stored column i with its sign XOR sg_i
-    u32 sg1 = 0u, sg2 = 0u, sg3 = 0u;
-    const u32 SIGN = 0x80000000u;
-    bool active = true;
-    double act = 1.0;
-    int iters = 0;
     const unsigned warp = 0xffffffffu;
+    double a = d.a, b = d.b, c = d.c, f = d.f, g = d.g, h = d.h;
+    DIso S;
+    S.s11 = d.s11; S.s12 = d.s12; S.s13 = d.s13; S.s21 = d.s21; S.s22 = d.s22; S.s23 = d.s23;
+    S.s31 = d.s31; S.s32 = d.s32; S.s33 = d.s33;
+    S.sg1 = S.x12 = S.x23 = S.x13 = 0u;
+    bool active = true;
+    int iters = 0;
     double sum = (((a + b) + f) + g) + h;
-
-    while (__any_sync(warp, active))
+    // binary64 while some unfinished lane still has a coefficient of 2^20 or more (the first trip
+    // always: the neighbor's coefficients are not sorted yet)
+    const double big = f32_tail ? 1048576.0 : 0.0;
+    bool more = true;
+    while (__any_sync(warp, more))
     {
         if (++iters > TB_REDUCE_CAP) break;
-
-        // a + b + f + g + h < 0                                      542-549
-        // (some lane of nearly every trip needs it, so it runs unconditionally with a 0/1 multiplier
-        //  instead of under a vote and a divergent branch)
-        {
-#ifdef TB_FIX_BRANCHY
-            const bool fix = active && sum < 0.0;
-            if (__any_sync(warp, fix))
-            {
-                if (fix)
-                {
-                    s13 += xflip(s11, sg1 ^ sg3) + xflip(s12, sg2 ^ sg3);
-                    s23 += xflip(s21, sg1 ^ sg3) + xflip(s22, sg2 ^ sg3);
-                    s33 += xflip(s31, sg1 ^ sg3) + xflip(s32, sg2 ^ sg3);
-                    c += sum;
-                    f += h + (b + b);
-                    g += h + (a + a);
-                }
-            }
-#else
-            const double fm = (active && sum < 0.0) ? 1.0 : 0.0;
-            const double m13 = xflip(fm, sg1 ^ sg3), m23 = xflip(fm, sg2 ^ sg3);
-            s13 = fma(m23, s12, fma(m13, s11, s13));
-            s23 = fma(m23, s22, fma(m13, s21, s23));
-            s33 = fma(m23, s32, fma(m13, s31, s33));
-            c = fma(fm, sum, c);
-            f = fma(fm, h + (b + b), f);
-            g = fma(fm, h + (a + a), g);
-#endif
-        }
-
-        // shear 1: col2 += t col1                                    551-567
-        const double den = a + a;
-        const double rden = rcp_f64(den);
-        {
-            const double t = dshear_t(a, h, den, rden, act);
-            const double ts = xflip(t, sg1 ^ sg2);
-            s12 = fma(ts, s11, s12); s22 = fma(ts, s21, s22); s32 = fma(ts, s31, s32);
-            const double temp = a * t;
-            h += temp;
-            b = fma(h, t, b);
-            f = fma(g, t, f);
-            h += temp;
-        }
-        // shear 2: col3 += t col2                                    569-585
-        {
-            const double den2 = b + b;
-            const double rden2 = rcp_f64(den2);
-            const double t = dshear_t(b, f, den2, rden2, act);
-            const double ts = xflip(t, sg2 ^ sg3);
-            s13 = fma(ts, s12, s13); s23 = fma(ts, s22, s23); s33 = fma(ts, s32, s33);
-            const double temp = b * t;
-            f += temp;
-            c = fma(f, t, c);
-            g = fma(h, t, g);
-            f += temp;
-        }
-        // shear 3: col3 += t col1 (a, hence 2a, is unchanged)         587-603
-        {
-            const double t = dshear_t(a, g, den, rden, act);
-            const double ts = xflip(t, sg1 ^ sg3);
-            s13 = fma(ts, s11, s13); s23 = fma(ts, s21, s23); s33 = fma(ts, s31, s33);
-            const double temp = a * t;
-            g += temp;
-            c = fma(g, t, c);
-            f = fma(h, t, f);
-            g += temp;
-        }
-
-        // sort a <= b <= c with the reference's tie-breaks            605-624
-        // (form pairs swap by select on the ALU pipe, isometry columns arithmetically on the
-        //  FP64 pipe: the two pipes are the kernel's co-limiters)
-        {
-            const bool p = active & ((a > b) | ((a == b) & (fabs(f) > fabs(g))));
-            const double m = p ? 1.0 : 0.0;
-            dswap_sel(p, a, b); dswap_sel(p, f, g);
-            dswap_fma(m, s11, s12); dswap_fma(m, s21, s22); dswap_fma(m, s31, s32);
-            const u32 pm = p ? SIGN : 0u, o1 = sg1;        // (c1,c2,c3) <- (-c2,-c1,-c3)
-            sg1 = (p ? sg2 : sg1) ^ pm; sg2 = (p ? o1 : sg2) ^ pm; sg3 ^= pm;
-        }
-        {
-            const bool p = active & ((b > c) | ((b == c) & (fabs(g) > fabs(h))));
-            const double m = p ? 1.0 : 0.0;
-            dswap_sel(p, b, c); dswap_sel(p, g, h);
-            dswap_fma(m, s12, s13); dswap_fma(m, s22, s23); dswap_fma(m, s32, s33);
-            const u32 pm = p ? SIGN : 0u, o2 = sg2;        // (c1,c2,c3) <- (-c1,-c3,-c2)
-            sg2 = (p ? sg3 : sg2) ^ pm; sg3 = (p ? o2 : sg3) ^ pm; sg1 ^= pm;
-        }
-        {
-            const bool p = active & ((a > b) | ((a == b) & (fabs(f) > fabs(g))));
-            const double m = p ? 1.0 : 0.0;
-            dswap_sel(p, a, b); dswap_sel(p, f, g);
-            dswap_fma(m, s11, s12); dswap_fma(m, s21, s22); dswap_fma(m, s31, s32);
-            const u32 pm = p ? SIGN : 0u, o1 = sg1;
-            sg1 = (p ? sg2 : sg1) ^ pm; sg2 = (p ? o1 : sg2) ^ pm; sg3 ^= pm;
-        }
-
-        // sign normalisation                                          626-687
-        // Restated: if f g h > 0 (all nonzero, evenly many negative) flip the negative ones;
-        // otherwise flip the positive ones and, when that is an odd number of flips, also the
-        // first zero among f, g, h (column flips must come in pairs: det stays +p^2).
-        {
-            const bool fneg = f < 0.0, gneg = g < 0.0, hneg = h < 0.0;
-            const bool fpos = f > 0.0, gpos = g > 0.0, hpos = h > 0.0;
-            const bool caseA = (f * g) * h > 0.0;
-            const bool oddB = !caseA & ((fpos != gpos) != hpos);
-            const bool fz = !fneg & !fpos, gz = !gneg & !gpos, hz = !hneg & !hpos;
-            const bool f1 = (caseA ? fneg : fpos) | (oddB & fz);
-            const bool f2 = (caseA ? gneg : gpos) | (oddB & !fz & gz);
-            const bool f3 = (caseA ? hneg : hpos) | (oddB & !fz & !gz & hz);
-            const u32 n1 = (active & f1) ? SIGN : 0u;
-            const u32 n2 = (active & f2) ? SIGN : 0u;
-            const u32 n3 = (active & f3) ? SIGN : 0u;
-            f = xflip(f, n1); g = xflip(g, n2); h = xflip(h, n3);
-            sg1 ^= n1; sg2 ^= n2; sg3 ^= n3;
-        }
-
-        // exit test                                                   689-690
-        sum = (((a + b) + f) + g) + h;
-        const bool done = (fabs(f) <= b) & (fabs(g) <= a) & (fabs(h) <= a) & (sum >= 0.0);
-        active = active & !done;
-        act = active ? 1.0 : 0.0;
+        reduce_trip<double>(a, b, c, f, g, h, sum, S, active);
+        more = active & (c >= big);
     }
-
-    d.a = a; d.b = b; d.c = c; d.f = f; d.g = g; d.h = h;
-    d.s11 = xflip(s11, sg1); d.s21 = xflip(s21, sg1); d.s31 = xflip(s31, sg1);
-    d.s12 = xflip(s12, sg2); d.s22 = xflip(s22, sg2); d.s32 = xflip(s32, sg2);
-    d.s13 = xflip(s13, sg3); d.s23 = xflip(s23, sg3); d.s33 = xflip(s33, sg3);
+    if (f32_tail)
+    {
+        float a4 = (float)a, b4 = (float)b, c4 = (float)c, f4 = (float)f, g4 = (float)g, h4 = (float)h;
+        float sum4 = (float)sum;
+        while (__any_sync(warp, active))
+        {
+            if (++iters > TB_REDUCE_CAP) break;
+            reduce_trip<float>(a4, b4, c4, f4, g4, h4, sum4, S, active);
+        }
+        d.on_boundary = boundary_fixup_fires(a4, b4, c4, f4, g4, h4);
+        d.a = (double)a4; d.b = (double)b4; d.c = (double)c4; d.f = (double)f4; d.g = (double)g4; d.h = (double)h4;
+    }
+    else
+    {
+        d.on_boundary = boundary_fixup_fires(a, b, c, f, g, h);
+        d.a = a; d.b = b; d.c = c; d.f = f; d.g = g; d.h = h;
+    }
+    const u32 sg2 = S.sg1 ^ S.x12, sg3 = S.sg1 ^ S.x13;
+    d.s11 = xflip(S.s11, S.sg1); d.s21 = xflip(S.s21, S.sg1); d.s31 = xflip(S.s31, S.sg1);
+    d.s12 = xflip(S.s12, sg2); d.s22 = xflip(S.s22, sg2); d.s32 = xflip(S.s32, sg2);
+    d.s13 = xflip(S.s13, sg3); d.s23 = xflip(S.s23, sg3); d.s33 = xflip(S.s33, sg3);
     return iters;
 }
 
 // Post-loop boundary fix-ups (QuadForm.h:693-764): rare, so plain branches, and out of line: the
-// hot path only asks whether the form lies on a boundary of the reduction domain at all
-// (on_boundary), which is the first clause of each of the ten fix-ups -- when none holds for the
-// form as the loop left it, none of them fires and nothing changes.
-#ifdef TB_BOUNDARY_INLINE      /* A/B timing: the fix-ups inlined into the hot path, as in round 1 */
-#define TB_BOUNDARY_ATTR __forceinline__
-#else
-#define TB_BOUNDARY_ATTR __noinline__
-#endif
+// hot path only asks whether any of them fires (boundary_fixup_fires) and calls this when one does.
 template <class Z>
-__device__ TB_BOUNDARY_ATTR void reduce_boundary(Form<Z> &q, Iso<Z> &s)
+__device__ __noinline__ void reduce_boundary(Form<Z> &q, Iso<Z> &s)
 {
     Z a = q.a, b = q.b, c = q.c, f = q.f, g = q.g, h = q.h, t;
     const Z zero = Z(0);
@@ -849,7 +924,8 @@ __device__ __forceinline__ bool reduce_out_of_line(Form<Z> &q, Iso<Z> &s)
 // the whole warp's operands are small, else the integer code.  Every lane of the
 // warp must call this (it votes).
 template <class Z>
-__device__ __forceinline__ bool reduce_neighbor(Form<Z> &q, Iso<Z> &s, bool fp64_allowed, bool proven_small)
+__device__ __forceinline__ bool reduce_neighbor(Form<Z> &q, Iso<Z> &s, bool fp64_allowed, bool proven_small,
+                                                bool f32_tail = false)
 {
     // proven_small: the host bounded everything build_neighbor can hand over below 2^50 for this launch
     // (PrimeCtx::proven_small), so the per-lane magnitude test and its vote are skipped
@@ -870,19 +946,13 @@ __device__ __forceinline__ bool reduce_neighbor(Form<Z> &q, Iso<Z> &s, bool fp64
     d.s11 = __ll2double_rn(s.a11.low64()); d.s12 = __ll2double_rn(s.a12.low64()); d.s13 = __ll2double_rn(s.a13.low64());
     d.s21 = __ll2double_rn(s.a21.low64()); d.s22 = __ll2double_rn(s.a22.low64()); d.s23 = __ll2double_rn(s.a23.low64());
     d.s31 = __ll2double_rn(s.a31.low64()); d.s32 = __ll2double_rn(s.a32.low64()); d.s33 = __ll2double_rn(s.a33.low64());
-    const int iters = reduce_loop_fp64(d);
-    // on a boundary of the reduction domain?  (first clauses of QuadForm.h:693, 702, 710, 718, 726, 732,
-    // 738, 744, 752; 759 repeats 744)
-    const bool on_boundary = ((((d.a + d.b) + d.f) + d.g) + d.h == 0.0) | (d.a == -d.h) | (d.a == -d.g) | (d.b == -d.f) |
-                             (d.a == d.h) | (d.a == d.g) | (d.b == d.f) | (d.a == d.b) | (d.b == d.c);
+    const int iters = reduce_loop_fp64(d, f32_tail);
+    const bool on_boundary = d.on_boundary;
     q.a = Z(__double2ll_rn(d.a)); q.b = Z(__double2ll_rn(d.b)); q.c = Z(__double2ll_rn(d.c));
     q.f = Z(__double2ll_rn(d.f)); q.g = Z(__double2ll_rn(d.g)); q.h = Z(__double2ll_rn(d.h));
     s.a11 = Z(__double2ll_rn(d.s11)); s.a12 = Z(__double2ll_rn(d.s12)); s.a13 = Z(__double2ll_rn(d.s13));
     s.a21 = Z(__double2ll_rn(d.s21)); s.a22 = Z(__double2ll_rn(d.s22)); s.a23 = Z(__double2ll_rn(d.s23));
     s.a31 = Z(__double2ll_rn(d.s31)); s.a32 = Z(__double2ll_rn(d.s32)); s.a33 = Z(__double2ll_rn(d.s33));
-#ifdef TB_BOUNDARY_INLINE
-    reduce_boundary(q, s);
-#else
     if (on_boundary)
     {
         Form<Z> tq = q;          // copies: only these are address-taken by the out-of-line call
@@ -891,7 +961,6 @@ __device__ __forceinline__ bool reduce_neighbor(Form<Z> &q, Iso<Z> &s, bool fp64
         q = tq;
         s = ts;
     }
-#endif
     return iters <= TB_REDUCE_CAP;
 }
 
@@ -1097,7 +1166,7 @@ __device__ __forceinline__ int one_neighbor(int n, u32 t, const RepPrime &rp, co
         o.s.a21 = zero; o.s.a22 = one; o.s.a23 = zero;
         o.s.a31 = zero; o.s.a32 = zero; o.s.a33 = one;
     }
-    if (!reduce_neighbor(o.q, o.s, pc.fp64_reduce != 0, pc.proven_small != 0)) status = NBR_OVERFLOW;
+    if (!reduce_neighbor(o.q, o.s, pc.fp64_reduce != 0, pc.proven_small != 0, pc.f32_tail != 0)) status = NBR_OVERFLOW;
 
     int r = genus_lookup(o.q, gc);                           // Genus.h:575
     if (r < 0)

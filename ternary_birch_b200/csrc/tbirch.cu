@@ -308,6 +308,8 @@ struct tb_genus {
 
     double lambda_min = 1.0;    // lower bound of the smallest Gram eigenvalue over all representatives
     double log2_coef = 0, log2_iso = 0, log2_scalar = 0;   // log2 of the largest |q|, |s| / |sinv|, scalar entries
+    double log2_mid = 0;          // log2 of the largest middle diagonal coefficient b (a <= b <= c on reduced forms)
+    double log2_isounit = 99;     // |entry of a reduced neighbor isometry| <= p * 2^log2_isounit (table loop below)
     double log2_mother = 0;                                // log2 of the largest |coefficient| of representative 0
     double mother_lambda = 0;                              // lower bound of the mother form's smallest Gram eigenvalue
     cudaStream_t stream = 0;
@@ -472,15 +474,30 @@ static int upload_table(tb_genus *g, const tb_genus_desc *d)
     }
     g->lambda_min = definite ? lam * 0.5 : 0.0;   // 0 disables the FP64 reduce loop
     {
-        double mq = 1, ms = 1, md = 1;
+        double mq = 1, ms = 1, md = 1, mb = 1;
         for (int n = 0; n < N; ++n)
         {
             const i64 *c = cur + (size_t)n * TB_REC_WORDS, *r = rep + (size_t)n * TB_REC_WORDS;
             for (int i = 0; i < 6; ++i) mq = std::max(mq, fabs((double)c[i]));
+            mb = std::max(mb, std::max(fabs((double)c[0]), fabs((double)c[1])));
             md = std::max(md, fabs((double)c[6]));
             for (int i = 7; i < 16; ++i) ms = std::max(ms, std::max(fabs((double)c[i]), fabs((double)r[i])));
         }
-        g->log2_coef = log2(mq); g->log2_iso = log2(ms); g->log2_scalar = log2(md);
+        g->log2_coef = log2(mq); g->log2_iso = log2(ms); g->log2_scalar = log2(md); g->log2_mid = log2(mb);
+        // Reduced neighbor isometry of representative n: column j is a vector v with Q_n(v) = p^2 d_j, d_j a diagonal
+        // coefficient of the representative that is hit.  With G_n the Gram matrix (v^T G_n v = 2 Q_n(v)) the largest
+        // v_i^2 on that ellipsoid is 2 p^2 d_j (G_n^-1)_ii, so |entry| <= p sqrt(2 D R), D = largest diagonal
+        // coefficient in the table, R = largest diagonal entry of any G_n^-1 (cofactor / determinant).
+        double R = 0, D = 1;
+        for (int n = 0; n < N && definite; ++n)
+        {
+            const i64 *c = cur + (size_t)n * TB_REC_WORDS;
+            const double a = (double)c[0], b = (double)c[1], cc = (double)c[2], f = (double)c[3], gg = (double)c[4], h = (double)c[5];
+            const double det = 2.0 * (4.0 * a * b * cc + f * gg * h - a * f * f - b * gg * gg - cc * h * h);
+            R = std::max(R, std::max((4.0 * b * cc - f * f) / det, std::max((4.0 * a * cc - gg * gg) / det, (4.0 * a * b - h * h) / det)));
+            D = std::max(D, std::max(a, std::max(b, cc)));
+        }
+        g->log2_isounit = (definite && R > 0) ? 0.5 * log2(2.0 * D * R) + 0.01 : 99.0;
         double mm = 1;
         for (int i = 0; i < 6; ++i) mm = std::max(mm, fabs((double)cur[i]));
         g->log2_mother = log2(mm);
@@ -697,10 +714,16 @@ static int setup_prime(tb_genus *g, uint64_t p)
         // isometry entries below 2 p^2.  Below 2^50 the FP64 loop needs no per-lane magnitude test.
         const double lp4 = log2((double)p + 4.0);
         pc.proven_small = (pc.fp64_reduce && g->lambda_min > 0 && g->log2_coef + 2 * lp4 + 2 < 50 && 2 * lp4 + 1 < 50) ? 1u : 0u;
-        // reduced neighbor isometries: columns v with Q_rep(v) = p^2 * (a coefficient), so |entry| <= p sqrt(A / lambda_min);
+        // reduced neighbor isometries: |entry| <= p * 2^log2_isounit (tb_genus_create);
         // with the table's own isometries below 2^31 as well, the trace of cur.s * s * rep.sinv needs 32-bit factors only
-        const double iso = g->lambda_min > 0 ? 1 + log2((double)p) + 0.5 * (g->log2_coef - log2(g->lambda_min)) : 99.0;
+        const double iso = log2((double)p) + g->log2_isounit;
         pc.iso32 = (pc.proven_small && iso < 31 && g->log2_iso < 31) ? 1u : 0u;
+        // binary32 tail of the reduce loop: a finished lane holds a reduced form (|f| <= b, |g|, |h| <= a <= b <= c)
+        // and is carried through the remaining trips with zero quotients, so its coefficients must be
+        // binary32 integers (c < 2^24) and its running sum a + b + f + g + h (<= 5 b) must stay exact (b < 2^20)
+        pc.f32_tail = (pc.fp64_reduce && g->log2_coef < 24 && g->log2_mid < 20) ? 1u : 0u;
+        if (getenv("TBIRCH_NO_F32_TAIL")) pc.f32_tail = 0u;                         // A/B switch: binary64 to the end
+        if (getenv("TBIRCH_NO_ISO32")) pc.iso32 = 0u;                                // A/B switch: 64-bit trace products
         if (getenv("TBIRCH_NO_PROVEN_BOUNDS")) pc.proven_small = pc.iso32 = 0u;   // A/B switch: the per-lane tests and 64-bit products
     }
     if (pc.use_lut)
@@ -811,7 +834,7 @@ static bool precise_bounds_ok(const tb_genus *g)
     if (!pc.fp64_reduce) return false;
     const double lp = log2((double)pc.p);
     const double build = 3 + g->log2_coef + 4 * lp;
-    const double iso = 1 + lp + 0.5 * (g->log2_coef - log2(g->lambda_min));
+    const double iso = std::min(1 + lp + 0.5 * (g->log2_coef - log2(g->lambda_min)), lp + g->log2_isounit);
     const double comp = 4 + 2 * g->log2_iso + iso;
     const double denom = lp + 2 * g->log2_scalar;
     const double spin_comp = 6 + 2 * g->log2_mother + std::max(comp, denom);
@@ -832,7 +855,7 @@ static bool precise_bounds_ok64(const tb_genus *g)
     const PrimeCtx &pc = g->ps.pc;
     if (!precise_bounds_ok(g) || !pc.narrow_trace || g->force_wide) return false;
     const double lp = log2((double)pc.p + 4.0);
-    const double iso = 1 + lp + 0.5 * (g->log2_coef - log2(g->lambda_min));
+    const double iso = std::min(1 + lp + 0.5 * (g->log2_coef - log2(g->lambda_min)), lp + g->log2_isounit);
     return lp < 20 && g->log2_coef + 2 * lp < 56 && iso < 60;
 }
 
@@ -847,6 +870,7 @@ static int launch_neighbors(tb_genus *g, int precise, int rep_begin, int rows, u
     L.P1 = g->ps.pc.p + 1;
     L.total = (u64)rows * L.P1;
     L.dP1 = make_invdiv(L.P1);
+    L.mP1 = L.total < (1ull << 32) ? (u64)(((unsigned __int128)1 << 64) / L.P1) + 1 : 0;
     L.rp = g->d_rp.ptr;
     L.W = W;
     L.records = records;

@@ -192,22 +192,19 @@ def test_row_shards_concatenate(genus):
 
 def test_int64_failure_modes(genus, golden_dir):
     """int64 mode at large p on the level-1062347 genus (tests/golden/errors.json holds what the
-    unmodified reference raises): p = 40009 overflows int64 in build_neighbor -> the reference's
-    overflow_error text.  p = 20011 also fails in both, but the reference fails EARLIER with
-    "Key not found." (rep 19, t 10737) because its `abs(int64_t)` resolves to the 32-bit
-    `abs(int)` (birch.h's include set) and truncates f = 4399578151 in reduce's exit test
-    (QuadForm.h:689); this implementation compares full 64-bit magnitudes, gets past that
-    neighbor and reports the genuine int64 overflow at rep 317 (documented in DESIGN.md 5)."""
+    unmodified reference raises): p = 20011 and p = 40009 overflow int64 in build_neighbor -> the
+    reference's overflow_error text, the same exception here.  (The reference compiled WITHOUT the
+    binding's <stdlib.h> prelude fails earlier at p = 20011 with "Key not found.": its abs(int64_t)
+    then resolves to abs(int) and truncates f = 4399578151 in reduce's exit test, QuadForm.h:689;
+    oracle/Makefile builds the checker the way the Cython binding is built)"""
     errors = json.load(open(golden_dir / "errors.json"))
     g = genus("1062347", False)
-    assert errors["L1062347_p40009_z64"]["kind"] == "overflow_error"
-    with pytest.raises(OverflowError) as info:
-        g.hecke_matrix_sparse(40009)
-    assert str(info.value) == errors["L1062347_p40009_z64"]["what"]
-    assert errors["L1062347_p20011_z64"]["kind"] == "invalid_argument"
-    with pytest.raises((OverflowError, ValueError)) as info:
-        g.hecke_matrix_sparse(20011)
-    assert str(info.value) in (errors["L1062347_p40009_z64"]["what"], "Key not found.")
+    for p in (40009, 20011):
+        want = errors[f"L1062347_p{p}_z64"]
+        assert want["kind"] == "overflow_error"
+        with pytest.raises(OverflowError) as info:
+            g.hecke_matrix_sparse(p)
+        assert str(info.value) == want["what"]
     # the checked 128-bit mode computes the same prime without error
     gp = genus("1062347", True)
     data, indices, indptr = gp.hecke_matrix_sparse(20011)[1]
@@ -434,6 +431,35 @@ def test_row_kernel_global_scratch_walks_rows(tables, port_oracle, monkeypatch, 
             assert_same_csr(g.hecke_matrix_sparse(p), port_oracle("1062347").hecke(p, False), (two_pass, p))
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("name,p", [("85085", 101), ("1062347", 1009), ("1009091", 107), ("11", 65521), ("85085", 9973), ("11", 7)])
+@pytest.mark.parametrize("env", [None, "TBIRCH_NO_F32_TAIL", "TBIRCH_NO_PROVEN_BOUNDS"])
+def test_reduce_loop_forms(tables, port_oracle, monkeypatch, name, p, env):
+    """The reduce loop has three exact forms chosen per launch from host-proven bounds: binary64 form +
+    int32 ring isometry with a binary32 tail (reduce_loop_mixed, the default wherever the bounds hold),
+    the same without the tail (TBIRCH_NO_F32_TAIL), and the all-binary64 loop (reduce_loop_fp64,
+    TBIRCH_NO_PROVEN_BOUNDS).  Each must reproduce the oracle's reduced forms AND isometries
+    (neighbor records), matrices and isometry stream, in both integer modes."""
+    from ternary_birch_b200 import Genus, IsometrySequence
+    for v in ("TBIRCH_NO_F32_TAIL", "TBIRCH_NO_PROVEN_BOUNDS"):
+        monkeypatch.delenv(v, raising=False)
+    if env:
+        monkeypatch.setenv(env, "1")
+    t = tables(name)
+    oracle = port_oracle(name)
+    rows = min(t.N, 32)
+    for precise in (False, True):
+        g = Genus(t, precise=precise)
+        try:
+            assert np.array_equal(g.neighbor_records(p, 0, rows), oracle.neighbor_records(p, precise)[:rows]), precise
+            assert_same_csr(g.hecke_matrix_sparse(p), oracle.hecke(p, precise), (name, p, precise, env))
+            if t.N * (p + 1) <= 200000:
+                seq = IsometrySequence(g, p)
+                assert np.array_equal(seq.read(t.N * (p + 1)), oracle.isometry_sequence(p, precise))
+                seq.close()
+        finally:
+            g.close()
 
 
 @pytest.mark.parametrize("name,p", [("85085", 101), ("1062347", 101), ("85085", 997)])
