@@ -45,7 +45,11 @@ struct PrimeCtx {
     u32 proven_small; // every value build_neighbor hands to the reduction is proven below 2^50 (no per-lane test)
     u32 iso32;        // table isometries and reduced neighbor isometries proven below 2^31 (32-bit products, int32 reduce isometry)
     u32 f32_tail;     // fp64_reduce and small table forms (c < 2^24, b < 2^20): the reduce loop finishes in binary32
+    u32 fast_setup;   // bit 0: the binary64 neighbor setup (fast_setup below) is exact for this launch; bit 1: the
+    u32 pad4;         //   reference's int64 arithmetic provably does not wrap, so int64 mode may use it (setup_prime)
     u64 pp;
+    double pd, ppd;   // p, p^2
+    double inv_pd, inv_ppd;   // RN(1 / p), RN(1 / p^2)
     InvDiv dp;        // division by p
     InvDiv dpp;       // division by p^2
     const u32 *inv_lut;   // [p] inverses mod p, or nullptr
@@ -920,15 +924,19 @@ __device__ __forceinline__ bool reduce_out_of_line(Form<Z> &q, Iso<Z> &s)
     return ok;
 }
 
-// Reduction entry point of the kernels: FP64 loop when the launch allows it and
-// the whole warp's operands are small, else the integer code.  Every lane of the
-// warp must call this (it votes).
+// The reduction in three steps, so that lanes whose neighbor was set up directly in binary64
+// (fast_setup) and lanes that went through the integer setup share one copy of the loop:
+//   reduce_prepare   integer form + isometry -> binary64 state, or (launch / warp not eligible) the
+//                    whole reduction in the integer code; every lane of the warp calls it (it votes)
+//   reduce_loop_fp64 the loop
+//   reduce_finish    binary64 state -> integers, boundary fix-ups
 template <class Z>
-__device__ __forceinline__ bool reduce_neighbor(Form<Z> &q, Iso<Z> &s, bool fp64_allowed, bool proven_small,
-                                                bool f32_tail = false)
+__device__ __forceinline__ bool reduce_prepare(Form<Z> &q, Iso<Z> &s, bool fp64_allowed, bool proven_small,
+                                               DReduce &d, bool &ok)
 {
     // proven_small: the host bounded everything build_neighbor can hand over below 2^50 for this launch
     // (PrimeCtx::proven_small), so the per-lane magnitude test and its vote are skipped
+    ok = true;
     if (!proven_small)
     {
         bool small = fits50(q.a) && fits50(q.b) && fits50(q.c) && fits50(q.f) && fits50(q.g) && fits50(q.h) &&
@@ -936,24 +944,25 @@ __device__ __forceinline__ bool reduce_neighbor(Form<Z> &q, Iso<Z> &s, bool fp64
                      fits50(s.a23) && fits50(s.a31) && fits50(s.a32) && fits50(s.a33) &&
                      q.a > Z(0) && q.b > Z(0);
         __syncwarp(0xffffffffu);
-        if (!(fp64_allowed && __all_sync(0xffffffffu, small))) return reduce_out_of_line(q, s);
+        if (!(fp64_allowed && __all_sync(0xffffffffu, small))) { ok = reduce_out_of_line(q, s); return false; }
     }
-    else if (!fp64_allowed) return reduce_out_of_line(q, s);
-
-    DReduce d;
+    else if (!fp64_allowed) { ok = reduce_out_of_line(q, s); return false; }
     d.a = __ll2double_rn(q.a.low64()); d.b = __ll2double_rn(q.b.low64()); d.c = __ll2double_rn(q.c.low64());
     d.f = __ll2double_rn(q.f.low64()); d.g = __ll2double_rn(q.g.low64()); d.h = __ll2double_rn(q.h.low64());
     d.s11 = __ll2double_rn(s.a11.low64()); d.s12 = __ll2double_rn(s.a12.low64()); d.s13 = __ll2double_rn(s.a13.low64());
     d.s21 = __ll2double_rn(s.a21.low64()); d.s22 = __ll2double_rn(s.a22.low64()); d.s23 = __ll2double_rn(s.a23.low64());
     d.s31 = __ll2double_rn(s.a31.low64()); d.s32 = __ll2double_rn(s.a32.low64()); d.s33 = __ll2double_rn(s.a33.low64());
-    const int iters = reduce_loop_fp64(d, f32_tail);
-    const bool on_boundary = d.on_boundary;
+    return true;
+}
+template <class Z>
+__device__ __forceinline__ void reduce_finish(const DReduce &d, Form<Z> &q, Iso<Z> &s)
+{
     q.a = Z(__double2ll_rn(d.a)); q.b = Z(__double2ll_rn(d.b)); q.c = Z(__double2ll_rn(d.c));
     q.f = Z(__double2ll_rn(d.f)); q.g = Z(__double2ll_rn(d.g)); q.h = Z(__double2ll_rn(d.h));
     s.a11 = Z(__double2ll_rn(d.s11)); s.a12 = Z(__double2ll_rn(d.s12)); s.a13 = Z(__double2ll_rn(d.s13));
     s.a21 = Z(__double2ll_rn(d.s21)); s.a22 = Z(__double2ll_rn(d.s22)); s.a23 = Z(__double2ll_rn(d.s23));
     s.a31 = Z(__double2ll_rn(d.s31)); s.a32 = Z(__double2ll_rn(d.s32)); s.a33 = Z(__double2ll_rn(d.s33));
-    if (on_boundary)
+    if (d.on_boundary)
     {
         Form<Z> tq = q;          // copies: only these are address-taken by the out-of-line call
         Iso<Z> ts = s;
@@ -961,6 +970,18 @@ __device__ __forceinline__ bool reduce_neighbor(Form<Z> &q, Iso<Z> &s, bool fp64
         q = tq;
         s = ts;
     }
+}
+// Reduction entry point of the genus-enumeration kernels: FP64 loop when the launch allows it and
+// the whole warp's operands are small, else the integer code.  Every lane of the warp must call this.
+template <class Z>
+__device__ __forceinline__ bool reduce_neighbor(Form<Z> &q, Iso<Z> &s, bool fp64_allowed, bool proven_small,
+                                                bool f32_tail = false)
+{
+    DReduce d;
+    bool ok;
+    if (!reduce_prepare(q, s, fp64_allowed, proven_small, d, ok)) return ok;
+    const int iters = reduce_loop_fp64(d, f32_tail);
+    reduce_finish(d, q, s);
     return iters <= TB_REDUCE_CAP;
 }
 
@@ -1123,6 +1144,126 @@ __device__ __forceinline__ Iso<Z> load_iso(const i64 *m)
 }
 
 // ---------------------------------------------------------------------------
+// Neighbor setup in binary64 (launches with PrimeCtx::fast_setup): t -> isotropic line -> neighbor
+// form and isometry, for the generic lane -- the line has z = 1 (NeighborManager.h:96-143 with
+// at != 0, ct != 0, t != p) and g' != 0 mod p (no rotation, NeighborManager.h:279-295) -- which is
+// all but about four lanes in p + 1.  The other lanes return false and take the integer code
+// (setup_general).  The integer code spends ~800 instructions per warp here, mostly emulating
+// 64-bit products and 2-by-1 divisions with IMAD; every quantity is an integer below 2^53 under
+// the launch's bounds, so DFMA computes it exactly:
+//   p < 2^16, table coefficients |q| <= B with B p^2 < 2^48 (proven_small):
+//     u, v <= p/2;  au, hu, hv, bv <= B p / 2;  temp <= B (p + 1);  aa <= B (p^2 + p + 1) 3/4;
+//     gg, hh <= B (3p/2 + 1);  (-hh) ginv < 2 B p^2;  (aa mod p^2) ginv < p^3 < 2^48;
+//     bb <= B (p^2 + p + 1);  hh + s1 gg < 2 B p^2;  gg + cc s2 < 2 B p^2.
+//   The two numerators that exceed 2^53, aa + s2 (gg + cc s2) < B p^4 and hh + s2 ff < 3 B p^3, are
+//   carried as an error-free product (hi, lo = fma(x, y, -hi)): the quotient estimate RN((hi + rest) / d)
+//   is off by a few units at most, the exact remainder hi - q d + rest + lo is a small multiple of d
+//   (both divisions are exact in the reference: NeighborManager.h:338-341) and corrects it.
+//   x mod d for |x| < 2^53: q = RN(x * RN(1/d)) by the 1.5 * 2^52 trick, r = fma(-q, d, x) exact in
+//   (-d, d), plus d if negative.  The reference's remainders are C-truncated and then shifted by
+//   "if (s < -d/2) s += d" (NeighborManager.h:309-312), i.e. with c = x mod d in [0, d):
+//   s = c - d if x < 0 and c >= d - floor(d/2), else c.
+// In int64 mode the reference's own arithmetic wraps modulo 2^64 (and its discriminant check then
+// fails, NeighborManager.h:344-354); fast_setup is only set when the host has bounded the largest
+// intermediate, s2 (gg + cc s2) + aa, below 2^63, so the exact value IS the reference's value and
+// the check passes by construction.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ u32 fp_mul16(u32 a, u32 b, const PrimeCtx &pc)
+{
+    const u32 x = a * b;
+    const u32 r = x - __umulhi(x, pc.m32) * pc.p;
+    return r >= pc.p ? r - pc.p : r;
+}
+__device__ __forceinline__ double rint52(double x)      // nearest integer, |x| < 2^51
+{
+    return __dadd_rn(__dadd_rn(x, 6755399441055744.0), -6755399441055744.0);
+}
+// x mod d in [0, d) for an integer |x| < 2^53 (d, inv = RN(1/d) launch constants)
+__device__ __forceinline__ double fmod_pos(double x, double d, double inv)
+{
+    const double q = rint52(x * inv);
+    const double r = __fma_rn(-q, d, x);
+    return r < 0.0 ? r + d : r;
+}
+// (hi + lo + rest) / d for an exact division: hi, lo an error-free product, |rest| < 2^52
+__device__ __forceinline__ double exact_div(double hi, double lo, double rest, double d, double inv)
+{
+    const double q = rint52((hi + rest) * inv);
+    const double e = (__fma_rn(-q, d, hi) + rest) + lo;      // exact: a small multiple of d
+    return q + rint52(e * inv);
+}
+
+__device__ __forceinline__ bool fast_setup(const i64 *cur, const RepPrime &rp, u32 t, const PrimeCtx &pc,
+                                           DReduce &d, u32 &vx, u32 &vy, u32 &vz)
+{
+    const u32 p = pc.p;
+    // line_for_t's generic branch
+    u32 at = fp_mul16(fp_add(fp_mul16(fp_sub(t, 1u, p), rp.b, pc), rp.delta, p), t, pc);
+    at = fp_add(at, rp.a0, p);
+    const u32 ct = fp_add(fp_mul16(fp_add(fp_mul16(rp.b, t, pc), rp.h, p), t, pc), rp.a, p);
+    bool generic = (t != p) & (at != 0u) & (ct != 0u);
+    const u32 ctc = generic ? ct : 1u;                      // keep the table index in range on the other lanes
+    const u32 tc = generic ? t : 0u;
+    const u32 inv = fp_mul16(at, __ldg(pc.inv_lut + ctc), pc);
+    vx = fp_add(rp.x0, fp_sub(inv, 1u, p), p);
+    vy = fp_add(fp_sub(rp.y0, tc, p), fp_mul16(tc, inv, pc), p);
+    vz = 1u;
+
+    // build_neighbor, z = 1 (NeighborManager.h:226-245)
+    const int half = (int)(p >> 1);
+    int ux = (int)vx, uy = (int)vy;
+    if (ux > half) ux -= (int)p;
+    if (uy > half) uy -= (int)p;
+    const double u = (double)ux, v = (double)uy;
+    const double a = __ll2double_rn(__ldg(cur + 0)), b = __ll2double_rn(__ldg(cur + 1)), c = __ll2double_rn(__ldg(cur + 2));
+    const double f = __ll2double_rn(__ldg(cur + 3)), g = __ll2double_rn(__ldg(cur + 4)), h = __ll2double_rn(__ldg(cur + 5));
+    const double P = pc.pd, PP = pc.ppd, iP = pc.inv_pd, iPP = pc.inv_ppd;
+    const double au = a * u, hu = h * u, hv = h * v, bv = b * v;
+    const double temp = (au + hv) + g;
+    const double aa = fma(v, bv + f, fma(u, temp, c));
+    const double gg = -(temp + au);
+    const double hh = fma(2.0, bv, f + hu);
+    double bb = b;
+    const double cc = a;
+    double ff = -h;
+
+    // g' mod p and its inverse (279-303)
+    const double gm = fmod_pos(gg, P, iP);
+    generic &= gm != 0.0;
+    const u32 gi = (u32)__double2loint(__dadd_rn(gm, 6755399441055744.0));
+    const u32 ginv_u = __ldg(pc.inv_lut + gi);
+    const double ginv = __hiloint2double(0x43300000, (int)ginv_u) - 4503599627370496.0;
+
+    // s1 = (-hh ginv) mod p, s2 = (-aa ginv) mod p^2, the reference's truncated / shifted residues (309-312)
+    const double c1 = fmod_pos(-hh * ginv, P, iP);
+    const double s1 = (hh > 0.0 && c1 >= P - (double)half) ? c1 - P : c1;
+    const double c2 = fmod_pos(fmod_pos(-aa, PP, iPP) * ginv, PP, iPP);
+    const double hpp = (double)(pc.pp >> 1);
+    const double s2 = (c2 >= PP - hpp) ? c2 - PP : c2;        // aa = Q(u, v, 1) > 0, so -aa ginv < 0
+
+    // 314-341
+    const double temp1 = cc * s1;
+    bb = fma(s1, ff + temp1, bb);
+    ff = fma(2.0, temp1, ff);
+    const double hh1 = fma(s1, gg, hh);
+    const double temp2 = cc * s2;
+    const double x2 = gg + temp2;
+    const double hi_a = s2 * x2, lo_a = __fma_rn(s2, x2, -hi_a);
+    const double hi_h = s2 * ff, lo_h = __fma_rn(s2, ff, -hi_h);
+    d.a = exact_div(hi_a, lo_a, aa, PP, iPP);
+    d.b = bb;
+    d.c = cc * PP;
+    d.f = ff * P;
+    d.g = fma(2.0, temp2, gg);
+    d.h = exact_div(hi_h, lo_h, hh1, P, iP);
+    // isometry: [[u, 0, -1], [v, 1, 0], [1, 0, 0]], col2 += s1 col3, col1 += s2 col3, col2 *= p, col3 *= p^2
+    d.s11 = u - s2; d.s12 = -s1 * P; d.s13 = -PP;
+    d.s21 = v;      d.s22 = P;       d.s23 = 0.0;
+    d.s31 = 1.0;    d.s32 = 0.0;     d.s33 = 0.0;
+    return generic;
+}
+
+// ---------------------------------------------------------------------------
 // One neighbor, start to finish: the loop body of Genus.h:567-618.
 // ---------------------------------------------------------------------------
 enum NeighborStatus { NBR_OK = 0, NBR_OVERFLOW = 1, NBR_NOT_FOUND = 2 };
@@ -1143,6 +1284,49 @@ struct Neighbor {
     bool composed;
 };
 
+// Integer setup of one neighbor (any prime, any line): the representative's form, the isotropic line
+// for t and the neighbor lattice; a neighbor that overflowed int64 is replaced by the representative's
+// own form with the identity.  Out of line: in launches with fast_setup only a few lanes come here.
+template <class Z>
+__device__ __noinline__ int setup_general_nl(int n, u32 t, const RepPrime &rp, const PrimeCtx &pc,
+                                             const GenusCtx &gc, Form<Z> &oq, Iso<Z> &os, u32 *line)
+{
+    int status = 0;
+    const i64 *cur = gc.cur + (size_t)n * TB_REC_WORDS;
+    const Form<Z> q = load_form<Z>(cur);
+    u32 vx, vy, vz;
+    line_for_t(rp, t, pc, vx, vy, vz);
+    Form<Z> nq;
+    Iso<Z> s;
+    if (!build_neighbor(q, vx, vy, vz, __ldg(gc.disc + n), pc, nq, s))
+    {
+        status = 1;                                          // NBR_OVERFLOW
+        const Z zero = Z(0), one = Z(1);
+        nq = q;
+        s.a11 = one; s.a12 = zero; s.a13 = zero;
+        s.a21 = zero; s.a22 = one; s.a23 = zero;
+        s.a31 = zero; s.a32 = zero; s.a33 = one;
+    }
+    oq = nq;
+    os = s;
+    line[0] = vx; line[1] = vy; line[2] = vz;
+    return status;
+}
+// (the caller's copies: only these are address-taken by the out-of-line call, the Neighbor stays in registers)
+template <class Z>
+__device__ __forceinline__ int setup_general(int n, u32 t, const RepPrime &rp, const PrimeCtx &pc,
+                                             const GenusCtx &gc, Neighbor<Z> &o)
+{
+    Form<Z> tq;
+    Iso<Z> ts;
+    u32 line[3];
+    const int status = setup_general_nl<Z>(n, t, rp, pc, gc, tq, ts, line);
+    o.q = tq;
+    o.s = ts;
+    o.vx = line[0]; o.vy = line[1]; o.vz = line[2];
+    return status;
+}
+
 // want_comp: also produce the composed isometry when r == n (IsometrySequence
 // has no r == n shortcut, IsometrySequence.h:63-69).
 template <class Z>
@@ -1155,18 +1339,32 @@ __device__ __forceinline__ int one_neighbor(int n, u32 t, const RepPrime &rp, co
     // status differs.
     int status = NBR_OK;
     const i64 *cur = gc.cur + (size_t)n * TB_REC_WORDS;
-    const Form<Z> q = load_form<Z>(cur);
-    line_for_t(rp, t, pc, o.vx, o.vy, o.vz);
-    if (!build_neighbor(q, o.vx, o.vy, o.vz, __ldg(gc.disc + n), pc, o.q, o.s))
+    DReduce d;
+    bool in_fp64;
+    // int64 mode additionally needs the no-wrap bit (its reference arithmetic wraps, the exact one does not)
+    if (CheckDisc<Z>::value ? pc.fast_setup == 3u : (pc.fast_setup & 1u) != 0u)     // launch-uniform
     {
-        status = NBR_OVERFLOW;
-        const Z zero = Z(0), one = Z(1);
-        o.q = q;
-        o.s.a11 = one; o.s.a12 = zero; o.s.a13 = zero;
-        o.s.a21 = zero; o.s.a22 = one; o.s.a23 = zero;
-        o.s.a31 = zero; o.s.a32 = zero; o.s.a33 = one;
+        in_fp64 = true;
+        if (!fast_setup(cur, rp, t, pc, d, o.vx, o.vy, o.vz))
+        {
+            // the few special lanes (t = p, a zero of the line's conic, a rotated neighbor): integer setup
+            bool ok;
+            status = setup_general<Z>(n, t, rp, pc, gc, o);
+            reduce_prepare(o.q, o.s, true, true, d, ok);
+        }
     }
-    if (!reduce_neighbor(o.q, o.s, pc.fp64_reduce != 0, pc.proven_small != 0, pc.f32_tail != 0)) status = NBR_OVERFLOW;
+    else
+    {
+        bool ok;
+        status = setup_general<Z>(n, t, rp, pc, gc, o);
+        in_fp64 = reduce_prepare(o.q, o.s, pc.fp64_reduce != 0, pc.proven_small != 0, d, ok);
+        if (!ok) status = NBR_OVERFLOW;
+    }
+    if (in_fp64)                                             // warp-uniform
+    {
+        if (reduce_loop_fp64(d, pc.f32_tail != 0) > TB_REDUCE_CAP) status = NBR_OVERFLOW;
+        reduce_finish(d, o.q, o.s);
+    }
 
     int r = genus_lookup(o.q, gc);                           // Genus.h:575
     if (r < 0)

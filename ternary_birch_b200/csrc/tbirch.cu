@@ -723,6 +723,20 @@ static int setup_prime(tb_genus *g, uint64_t p)
         // binary32 integers (c < 2^24) and its running sum a + b + f + g + h (<= 5 b) must stay exact (b < 2^20)
         pc.f32_tail = (pc.fp64_reduce && g->log2_coef < 24 && g->log2_mid < 20) ? 1u : 0u;
         if (getenv("TBIRCH_NO_F32_TAIL")) pc.f32_tail = 0u;                         // A/B switch: binary64 to the end
+        // binary64 neighbor setup (fast_setup, tb_neighbor.cuh): bit 0 = exact (p < 2^16 with the inverse table,
+        // proven_small's B p^2 < 2^48); bit 1 = the reference's int64 arithmetic provably does not wrap, so int64
+        // mode may use it too: the largest intermediate of NeighborManager.h:207-341 on a z = 1, unrotated line is
+        // aa + s2 (gg + cc s2) <= B p^2 + p^2 (B (3p/2 + 1) + Bmid p^2) with |s2| < p^2 and cc = a <= Bmid
+        pc.pd = (double)p; pc.ppd = (double)(p * p);
+        pc.inv_pd = 1.0 / pc.pd; pc.inv_ppd = 1.0 / pc.ppd;
+        if (pc.m32 && pc.use_lut && pc.proven_small && pc.fp64_reduce)
+        {
+            const unsigned __int128 B = (unsigned __int128)ceil(exp2(g->log2_coef)) + 1, Bm = (unsigned __int128)ceil(exp2(g->log2_mid)) + 1;
+            const unsigned __int128 P = p, PP = P * P;
+            const unsigned __int128 worst = B * PP + PP * (B * (3 * P / 2 + 2) + Bm * PP);
+            pc.fast_setup = 1u | (worst < ((unsigned __int128)1 << 63) ? 2u : 0u);
+        }
+        if (getenv("TBIRCH_NO_FAST_SETUP")) pc.fast_setup = 0u;                      // A/B switch: integer setup on every lane
         if (getenv("TBIRCH_NO_ISO32")) pc.iso32 = 0u;                                // A/B switch: 64-bit trace products
         if (getenv("TBIRCH_NO_PROVEN_BOUNDS")) pc.proven_small = pc.iso32 = 0u;   // A/B switch: the per-lane tests and 64-bit products
     }
