@@ -695,6 +695,7 @@ __device__ __forceinline__ u64 parity_bytes(u32 spin, int kc)
     return v;
 }
 
+template <bool NARROW>
 __global__ void __launch_bounds__(512, 2) rows_acc_kernel(const __grid_constant__ RowLaunch L)
 {
     extern __shared__ u32 smem[];
@@ -784,83 +785,55 @@ __global__ void __launch_bounds__(512, 2) rows_acc_kernel(const __grid_constant_
             for (int j = tid; j < ncols; j += nt) runlen[j] = (unsigned char)(acc_lo[j] & 0xffu);
 
         // ---- D: entries, ascending columns, zeros dropped -----------------------------
-        int cnt[8];
-        i64 wbase[8];
+        // A class of column r has, per conductor kk of the chunk, the entry run - 2 odd_kk; it is stored iff
+        // lut[kc+kk][r] != -1 (inc bit) and 2 odd_kk != run.  All eight tests are done at once on the counter
+        // bytes: with hf = run / 2 in every byte, a byte of (counters ^ hf) is zero exactly where the entry
+        // is (an odd run has none), and the exact zero-byte mask ~(((x & 0x7f..) + 0x7f..) | x | 0x7f..)
+        // marks those.  The count sweep just adds the resulting 0/1 bytes per lane (no ballots); the store
+        // sweep takes one ballot per conductor for the positions.
+        u32 rowmask = 0u;                                                    // conductors of the chunk that contain row n (uniform)
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) { cnt[kk] = 0; wbase[kk] = 0; }
-        int mx = 0;
-        for (int pass = 0; pass < 2; ++pass)
+        for (int kk = 0; kk < 8; ++kk) if (kk < nk && s_npos[kk] != -1) rowmask |= 1u << kk;
+        const u32 rowb_lo = ((rowmask & 15u) * 0x00204081u) & 0x01010101u;   // bit kk -> byte kk
+        const u32 rowb_hi = ((rowmask >> 4) * 0x00204081u) & 0x01010101u;
+        // -- count
         {
-            for (int i = ibeg; i < iend; ++i)
+            u32 cl = 0u, ch = 0u;                                            // byte lanes, folded into cnt every 255 words
+            int cnt[8];
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) cnt[kk] = 0;
+            int mx = 0;
+            for (int i0 = ibeg; i0 < iend; i0 += 255)
             {
-                const u32 m = mask[i];
-                const bool hit = (m >> lane) & 1u;
-                const int j = wprefix[i] + __popc(m & lt);
-                const int r = i * 32 + lane;
-                u32 lo = 0u, hi = 0u, run = 0u, inc = 0u;
-                if (hit)
+                const int i1 = min(iend, i0 + 255);
+                for (int i = i0; i < i1; ++i)
                 {
-                    TB_CHECK(j >= 0 && j < ncols && r < L.N);
-                    lo = acc_lo[j];
-                    hi = both ? acc_hi[j] : 0u;
-                    run = kc == 0 ? (lo & 0xffu) : (u32)runlen[j];
+                    const u32 m = mask[i];
+                    if (!((m >> lane) & 1u)) continue;
+                    const int j = wprefix[i] + __popc(m & lt);
+                    TB_CHECK(j >= 0 && j < ncols && i * 32 + lane < L.N);
+                    u32 lo = acc_lo[j];
+                    const u32 hi = both ? acc_hi[j] : 0u;
+                    const u32 run = kc == 0 ? (lo & 0xffu) : (u32)runlen[j];
                     if (kc == 0) lo &= ~0xffu;
-                    inc = L.incl[(size_t)(kc >> 3) * L.N + r];           // bit kk: lut[kc + kk][r] != -1
-                }
-                if (pass == 0)
-                {
+                    const u32 inc = L.incl[(size_t)(kc >> 3) * L.N + i * 32 + lane];     // bit kk: lut[kc + kk][r] != -1
                     mx = max(mx, (int)run);
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)
-                    {
-                        if (kk >= nk) break;
-                        const u32 odd = ((kk < 4 ? lo : hi) >> (8 * (kk & 3))) & 0xffu;
-                        const bool nz = hit && ((inc >> kk) & 1u) && (2u * odd != run);
-                        cnt[kk] += __popc(__ballot_sync(0xffffffffu, nz));
-                    }
+                    const u32 hf = (run >> 1) * 0x01010101u;
+                    const u32 xl = lo ^ hf, xh = hi ^ hf;
+                    u32 zl = ~(((xl & 0x7f7f7f7fu) + 0x7f7f7f7fu) | xl | 0x7f7f7f7fu);  // 0x80 where 2 odd == run (even run)
+                    u32 zh = ~(((xh & 0x7f7f7f7fu) + 0x7f7f7f7fu) | xh | 0x7f7f7f7fu);
+                    if (run & 1u) { zl = 0u; zh = 0u; }
+                    cl += ~(zl >> 7) & ((inc & 15u) * 0x00204081u) & rowb_lo;
+                    ch += ~(zh >> 7) & ((inc >> 4) * 0x00204081u) & rowb_hi;
                 }
-                else
-                {
-                    int rp[8];
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) rp[kk] = -1;
-                    if (hit && inc)
-                    {
-                        const int *src = L.lutT + ((size_t)r << L.K) + kc;
-                        if (nk == 8)
-                        {
-                            const int4 x = __ldg(reinterpret_cast<const int4 *>(src));
-                            const int4 y = __ldg(reinterpret_cast<const int4 *>(src) + 1);
-                            rp[0] = x.x; rp[1] = x.y; rp[2] = x.z; rp[3] = x.w;
-                            rp[4] = y.x; rp[5] = y.y; rp[6] = y.z; rp[7] = y.w;
-                        }
-                        else
-                        {
-#pragma unroll
-                            for (int kk = 0; kk < 8; ++kk) if (kk < nk) rp[kk] = __ldg(src + kk);
-                        }
-                    }
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)
-                    {
-                        if (kk >= nk || s_npos[kk] == -1) continue;                  // Genus.h:624-625 (warp-uniform)
-                        const u32 odd = ((kk < 4 ? lo : hi) >> (8 * (kk & 3))) & 0xffu;
-                        const int value = (int)run - 2 * (int)odd;
-                        const bool nz = hit && rp[kk] != -1 && value != 0;
-                        const unsigned ballot = __ballot_sync(0xffffffffu, nz);
-                        if (nz)
-                        {
-                            const i64 at = wbase[kk] + cnt[kk] + __popc(ballot & lt);
-                            TB_CHECK(at >= 0 && at < L.extent && rp[kk] >= 0);
-                            if (L.idx16) { L.idx16[at] = (unsigned short)rp[kk]; L.dat8[at] = (signed char)value; }
-                            else { L.data[at] = value; L.indices[at] = rp[kk]; }
-                        }
-                        cnt[kk] += __popc(ballot);
-                    }
-                }
+                for (int kk = 0; kk < 4; ++kk) { cnt[kk] += (int)((cl >> (8 * kk)) & 0xffu); cnt[4 + kk] += (int)((ch >> (8 * kk)) & 0xffu); }
+                cl = 0u; ch = 0u;
             }
-            if (pass == 1) break;
-            // per-warp totals -> this row's totals -> chained offsets
+            // per-lane counts -> per-warp totals -> this row's totals -> chained offsets
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+                for (int o = 16; o; o >>= 1) cnt[kk] += __shfl_xor_sync(0xffffffffu, cnt[kk], o);
             if (lane == 0)
             {
 #pragma unroll
@@ -871,42 +844,105 @@ __global__ void __launch_bounds__(512, 2) rows_acc_kernel(const __grid_constant_
                 for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                 if (lane == 0 && mx > s_maxrun) atomicMax(&s_maxrun, mx);
             }
-            __syncthreads();
-            if (tid < nk)
+        }
+        __syncthreads();
+        if (tid < nk)
+        {
+            const int k = kc + tid;
+            i64 total = 0;
+            if (s_npos[tid] != -1)
+                for (int ww = 0; ww < nw; ++ww) total += warp_cnt[tid * 32 + ww];
+            u64 *state = L.lookback + (size_t)k * L.rows;
+            const u64 FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VALUE = (1ull << 62) - 1;
+            if (lrow > 0) atomicExch(state + lrow, FLAG_AGG | (u64)total);
+            i64 excl = 0;
+            for (int j = lrow - 1; j >= 0; )
             {
-                const int k = kc + tid;
-                i64 total = 0;
-                if (s_npos[tid] != -1)
-                    for (int ww = 0; ww < nw; ++ww) total += warp_cnt[tid * 32 + ww];
-                u64 *state = L.lookback + (size_t)k * L.rows;
-                const u64 FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VALUE = (1ull << 62) - 1;
-                if (lrow > 0) atomicExch(state + lrow, FLAG_AGG | (u64)total);
-                i64 excl = 0;
-                for (int j = lrow - 1; j >= 0; )
-                {
-                    const u64 v = *(volatile u64 *)(state + j);
-                    const u64 flag = v >> 62;
-                    if (flag == 0) continue;                 // predecessor still counting
-                    excl += (i64)(v & VALUE);
-                    if (flag == 2) break;                    // inclusive prefix: done
-                    --j;
-                }
-                const i64 incl_total = excl + total;
-                atomicExch(state + lrow, FLAG_INC | (u64)incl_total);
-                s_base[tid] = L.nnzbase[k] + excl;
-                if (s_npos[tid] != -1)
-                    (L.indptr_all + L.rowbase[k])[s_npos[tid] - L.rowfirst[k] + 1] = (int)incl_total;
-                if (lrow == L.rows - 1) L.nnz_out[k] = incl_total;
+                const u64 v = *(volatile u64 *)(state + j);
+                const u64 flag = v >> 62;
+                if (flag == 0) continue;                 // predecessor still counting
+                excl += (i64)(v & VALUE);
+                if (flag == 2) break;                    // inclusive prefix: done
+                --j;
             }
-            if (kc == 0 && tid == 32 && L.maxmult && s_maxrun > *(volatile int *)L.maxmult) atomicMax(L.maxmult, s_maxrun);
-            __syncthreads();
+            const i64 incl_total = excl + total;
+            atomicExch(state + lrow, FLAG_INC | (u64)incl_total);
+            s_base[tid] = L.nnzbase[k] + excl;
+            if (s_npos[tid] != -1)
+                (L.indptr_all + L.rowbase[k])[s_npos[tid] - L.rowfirst[k] + 1] = (int)incl_total;
+            if (lrow == L.rows - 1) L.nnz_out[k] = incl_total;
+        }
+        if (kc == 0 && tid == 32 && L.maxmult && s_maxrun > *(volatile int *)L.maxmult) atomicMax(L.maxmult, s_maxrun);
+        __syncthreads();
+        // -- store
+        {
+            i64 wbase[8];                                        // this warp's next position in conductor kk's output
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
             {
                 int before = 0;
                 for (int ww = 0; ww < w; ++ww) before += warp_cnt[kk * 32 + ww];
                 wbase[kk] = s_base[kk] + before;
-                cnt[kk] = 0;
+            }
+            for (int i = ibeg; i < iend; ++i)
+            {
+                const u32 m = mask[i];
+                if (m == 0u) continue;                                   // warp-uniform
+                const bool hit = (m >> lane) & 1u;
+                const int r = i * 32 + lane;
+                u32 lo = 0u, hi = 0u, run = 0u, inc = 0u;
+                if (hit)
+                {
+                    const int j = wprefix[i] + __popc(m & lt);
+                    lo = acc_lo[j];
+                    hi = both ? acc_hi[j] : 0u;
+                    run = kc == 0 ? (lo & 0xffu) : (u32)runlen[j];
+                    if (kc == 0) lo &= ~0xffu;
+                    inc = L.incl[(size_t)(kc >> 3) * L.N + r];
+                }
+                const u32 hf = (run >> 1) * 0x01010101u;
+                const u32 xl = lo ^ hf, xh = hi ^ hf;
+                u32 zl = ~(((xl & 0x7f7f7f7fu) + 0x7f7f7f7fu) | xl | 0x7f7f7f7fu);
+                u32 zh = ~(((xh & 0x7f7f7f7fu) + 0x7f7f7f7fu) | xh | 0x7f7f7f7fu);
+                if (run & 1u) { zl = 0u; zh = 0u; }
+                const u32 nl = ~(zl >> 7) & ((inc & 15u) * 0x00204081u) & rowb_lo;      // inc = 0 on lanes without a class
+                const u32 nh = ~(zh >> 7) & ((inc >> 4) * 0x00204081u) & rowb_hi;
+                int rp[8];
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) rp[kk] = -1;
+                if (nl | nh)
+                {
+                    const int *src = L.lutT + ((size_t)r << L.K) + kc;
+                    if (nk == 8)
+                    {
+                        const int4 x = __ldg(reinterpret_cast<const int4 *>(src));
+                        const int4 y = __ldg(reinterpret_cast<const int4 *>(src) + 1);
+                        rp[0] = x.x; rp[1] = x.y; rp[2] = x.z; rp[3] = x.w;
+                        rp[4] = y.x; rp[5] = y.y; rp[6] = y.z; rp[7] = y.w;
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) if (kk < nk) rp[kk] = __ldg(src + kk);
+                    }
+                }
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                {
+                    if (kk >= nk || !((rowmask >> kk) & 1u)) continue;               // Genus.h:624-625 (warp-uniform)
+                    const bool nz = ((kk < 4 ? nl : nh) >> (8 * (kk & 3))) & 1u;
+                    const unsigned ballot = __ballot_sync(0xffffffffu, nz);
+                    if (nz)
+                    {
+                        const u32 odd = ((kk < 4 ? lo : hi) >> (8 * (kk & 3))) & 0xffu;
+                        const int value = (int)run - 2 * (int)odd;
+                        const i64 at = wbase[kk] + (i64)__popc(ballot & lt);
+                        TB_CHECK(at >= 0 && at < L.extent && rp[kk] >= 0 && value != 0);
+                        if (NARROW) { L.idx16[at] = (unsigned short)rp[kk]; L.dat8[at] = (signed char)value; }
+                        else { L.data[at] = value; L.indices[at] = rp[kk]; }
+                    }
+                    wbase[kk] += (i64)__popc(ballot);
+                }
             }
         }
     }

@@ -1061,8 +1061,10 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     if (!(attrs_mask.load() & (1ull << (attr_dev & 63))))
     {
         const int optin = 218 * 1024;   // 227 KB per CTA minus the kernels' static shared memory (8 KB parity table)
-        TB_CUDA(cudaFuncSetAttribute(rows_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
-        TB_CUDA(cudaFuncSetAttribute(rows_acc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TB_CUDA(cudaFuncSetAttribute(rows_acc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+        TB_CUDA(cudaFuncSetAttribute(rows_acc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TB_CUDA(cudaFuncSetAttribute(rows_acc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+        TB_CUDA(cudaFuncSetAttribute(rows_acc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         TB_CUDA(cudaFuncSetAttribute(rows_kernel<ROWS_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
@@ -1104,7 +1106,8 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
         R.extent = std::max<int64_t>(off, 1);
         for (;;)
         {
-            if (use_acc) rows_acc_kernel<<<(unsigned)rows, threads, smem_acc, g->stream>>>(R);
+            if (use_acc && R.idx16) rows_acc_kernel<true><<<(unsigned)rows, threads, smem_acc, g->stream>>>(R);
+            else if (use_acc) rows_acc_kernel<false><<<(unsigned)rows, threads, smem_acc, g->stream>>>(R);
             else if (R.scratch) rows_kernel<ROWS_FUSED, true><<<row_grid, threads, 0, g->stream>>>(R);
             else rows_kernel<ROWS_FUSED><<<row_grid, threads, smem, g->stream>>>(R);
             ++g_launches;
