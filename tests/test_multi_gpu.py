@@ -54,7 +54,7 @@ def _worker(rank, world, port, result_path, name, p, precise, narrow):
             ok, why = False, f"expected the 3-byte form on every rank, got {info['entry_bytes']}"
     res.close()
     # (2) prime axis: rank r computes a different prime; rank 0 receives every T_p whole
-    primes = shard.prime_shards([p, 19, 23, 29][:world], world)
+    primes = shard.prime_shards([p, 29, 31, 37][:world], world)          # none divides a golden level
     mine = primes[rank][0]
     res = g.hecke_device(mine)
     got = shard.gather_hecke_device(res, dev)
