@@ -375,7 +375,10 @@ def main():
     # warm-up: W untimed steps, at least eight: both pinned result sets must have been written by the host
     # once (the first CPU store to a page of a fresh cudaHostAlloc mapping takes a minor fault), and the library
     # measures one read-back in each format before it settles on one (tb_readback_stats)
-    for i in range(max(8, args.warmup)):
+    # (with several ranks per host the per-rank format choices settle against each other: at 8 ranks the
+    #  measured steps were 340 ms for the first ten and 162 ms from then on, profiles/README.md r2y)
+    e2e_warmup = max(8 if world == 1 else 24, args.warmup)
+    for i in range(e2e_warmup):
         step_e2e(i)
     drain(0)
     drain(1)
@@ -516,7 +519,7 @@ def main():
                     roofline=roofline, cpu_baseline=cpu,
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
                              result_bytes_per_step=result_bytes,
-                             step_wall_ms=my_steps,
+                             warmup_steps=e2e_warmup, step_wall_ms=my_steps,
                              slowest_rank_step_wall_ms=max((r["steps"] for r in per_rank), key=lambda v: sum(v[:-1])),
                              readback="per rank, chosen from measured delivery rates (tb_readback_stats): uint16 column + int8 "
                                       "entry over PCIe widened to the reference's int32 CSR by host threads, or int32 CSR over PCIe",
