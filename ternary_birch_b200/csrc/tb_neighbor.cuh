@@ -666,12 +666,15 @@ __device__ __forceinline__ double rwide(float t) { return (double)t; }
 // floor((x - y) / den), see above; a finished lane has rden = 0, hence quotient 0 (its remainder
 // x - y is a - h, b - f or a - g of a form that passed the exit test: never negative)
 template <class F>
-__device__ __forceinline__ F shear_quot(F x, F y, F den, F rden)
+__device__ __forceinline__ F shear_quot(F x, F y, F den, F rden, int &ti)
 {
     const F num = x - y;
-    const F q = radd(rfma(num, rden, rmagic(F(0))), -rmagic(F(0)));
+    const F qm = rfma(num, rden, rmagic(F(0)));
+    const F q = radd(qm, -rmagic(F(0)));
     const F r = rfma(-q, den, num);            // exact
-    return q + rcorr(F(0), rsign(r));          // q - 1 if r < 0 (sign mask of r ANDed into the bits of -1.0)
+    const int m = rsign(r);
+    ti = rquot(qm) + m;                        // the same quotient as an int32 (free: the low word of q + 1.5 * 2^52)
+    return q + rcorr(F(0), m);                 // q - 1 if r < 0 (sign mask of r ANDed into the bits of -1.0)
 }
 template <class F>
 __device__ __forceinline__ void rswap(bool p, F &x, F &y)
@@ -691,13 +694,95 @@ __device__ __forceinline__ void rswap(bool p, F &x, F &y)
 struct DIso {
     double s11, s12, s13, s21, s22, s23, s31, s32, s33;
     u32 sg1, x12, x23, x13;
+
+    __device__ __forceinline__ void load(const double *v)
+    {
+        s11 = v[0]; s12 = v[1]; s13 = v[2]; s21 = v[3]; s22 = v[4]; s23 = v[5]; s31 = v[6]; s32 = v[7]; s33 = v[8];
+        sg1 = x12 = x23 = x13 = 0u;
+    }
+    __device__ __forceinline__ void fix(bool on)                         // col3 += col1 + col2
+    {
+        const double fd = on ? 1.0 : 0.0;
+        const double m13 = xflip(fd, x13), m23 = xflip(fd, x23);
+        s13 = fma(m23, s12, fma(m13, s11, s13));
+        s23 = fma(m23, s22, fma(m13, s21, s23));
+        s33 = fma(m23, s32, fma(m13, s31, s33));
+    }
+    __device__ __forceinline__ void shear12(double t, int) { const double ts = xflip(t, x12); s12 = fma(ts, s11, s12); s22 = fma(ts, s21, s22); s32 = fma(ts, s31, s32); }
+    __device__ __forceinline__ void shear23(double t, int) { const double ts = xflip(t, x23); s13 = fma(ts, s12, s13); s23 = fma(ts, s22, s23); s33 = fma(ts, s32, s33); }
+    __device__ __forceinline__ void shear13(double t, int) { const double ts = xflip(t, x13); s13 = fma(ts, s11, s13); s23 = fma(ts, s21, s23); s33 = fma(ts, s31, s33); }
+    __device__ __forceinline__ void swap12(bool p)                       // (c1,c2,c3) <- (-c2,-c1,-c3)
+    {
+        const double m = p ? 1.0 : 0.0;
+        dswap_fma(m, s11, s12); dswap_fma(m, s21, s22); dswap_fma(m, s31, s32);
+        const u32 o23 = x23;
+        sg1 ^= p ? (x12 ^ 0x80000000u) : 0u; x23 = p ? x13 : x23; x13 = p ? o23 : x13;
+    }
+    __device__ __forceinline__ void swap23(bool p)                       // (c1,c2,c3) <- (-c1,-c3,-c2)
+    {
+        const double m = p ? 1.0 : 0.0;
+        dswap_fma(m, s12, s13); dswap_fma(m, s22, s23); dswap_fma(m, s32, s33);
+        const u32 o12 = x12;
+        sg1 ^= p ? 0x80000000u : 0u; x12 = p ? x13 : x12; x13 = p ? o12 : x13;
+    }
+    __device__ __forceinline__ void negate(u32 n1, u32 n2, u32 n3)        // sign-bit masks of the columns to negate
+    {
+        sg1 ^= n1; x12 ^= n1 ^ n2; x23 ^= n2 ^ n3; x13 ^= n1 ^ n3;
+    }
+};
+
+// The same isometry in int32 ring arithmetic (launches with PrimeCtx::iso32).  The column operations
+// are ring operations (add, multiply by an integer), so they can run modulo 2^32: the host has proven
+// that every entry of the isometry the loop ENDS with is below 2^31 in magnitude, hence the wrapped
+// result is the result, whatever the intermediates did.  That takes 42 of the 115 FP64-pipe
+// instructions of a binary64 trip (the pipe that stage saturates) to IMAD on the otherwise idle FMA
+// pipe, halves the isometry's registers and needs no lazy signs: a conditional swap-and-negate of
+// columns i, j is  u = c_i + c_j; c_i -= m u; c_j -= m u  with m = 1 or 0.
+struct IIso {
+    int s11, s12, s13, s21, s22, s23, s31, s32, s33;
+
+    __device__ __forceinline__ void load(const double *v)
+    {
+        s11 = __double2int_rn(v[0]); s12 = __double2int_rn(v[1]); s13 = __double2int_rn(v[2]);
+        s21 = __double2int_rn(v[3]); s22 = __double2int_rn(v[4]); s23 = __double2int_rn(v[5]);
+        s31 = __double2int_rn(v[6]); s32 = __double2int_rn(v[7]); s33 = __double2int_rn(v[8]);
+    }
+    __device__ __forceinline__ void fix(bool on)
+    {
+        const int fi = on ? 1 : 0;
+        s13 += fi * (s11 + s12); s23 += fi * (s21 + s22); s33 += fi * (s31 + s32);
+    }
+    __device__ __forceinline__ void shear12(double, int t) { s12 += t * s11; s22 += t * s21; s32 += t * s31; }
+    __device__ __forceinline__ void shear23(double, int t) { s13 += t * s12; s23 += t * s22; s33 += t * s32; }
+    __device__ __forceinline__ void shear13(double, int t) { s13 += t * s11; s23 += t * s21; s33 += t * s31; }
+    static __device__ __forceinline__ void swapneg(int m, int nu, int &ci, int &cj, int &ck)
+    {
+        const int u = ci + cj;
+        ci -= m * u; cj -= m * u; ck *= nu;
+    }
+    __device__ __forceinline__ void swap12(bool p)
+    {
+        const int m = p ? 1 : 0, nu = 1 - 2 * m;
+        swapneg(m, nu, s11, s12, s13); swapneg(m, nu, s21, s22, s23); swapneg(m, nu, s31, s32, s33);
+    }
+    __device__ __forceinline__ void swap23(bool p)
+    {
+        const int m = p ? 1 : 0, nu = 1 - 2 * m;
+        swapneg(m, nu, s12, s13, s11); swapneg(m, nu, s22, s23, s21); swapneg(m, nu, s32, s33, s31);
+    }
+    __device__ __forceinline__ void negate(u32 n1, u32 n2, u32 n3)
+    {
+        s11 = n1 ? -s11 : s11; s21 = n1 ? -s21 : s21; s31 = n1 ? -s31 : s31;
+        s12 = n2 ? -s12 : s12; s22 = n2 ? -s22 : s22; s32 = n2 ? -s32 : s32;
+        s13 = n3 ? -s13 : s13; s23 = n3 ? -s23 : s23; s33 = n3 ? -s33 : s33;
+    }
 };
 
 // One trip on every lane of the warp; finished lanes are frozen: their reciprocals (hence shear
 // quotients) and swap predicates are masked, the fix step and the sign normalisation cannot fire on
 // them (exit test: sum >= 0; normalisation is idempotent).
-template <class F>
-__device__ __forceinline__ void reduce_trip(F &a, F &b, F &c, F &f, F &g, F &h, F &sum, DIso &S, bool &active)
+template <class F, class ISO>
+__device__ __forceinline__ void reduce_trip(F &a, F &b, F &c, F &f, F &g, F &h, F &sum, ISO &S, bool &active)
 {
     const F zero = F(0), one = F(1);
     const u32 SIGN = 0x80000000u;
@@ -707,22 +792,18 @@ __device__ __forceinline__ void reduce_trip(F &a, F &b, F &c, F &f, F &g, F &h, 
     {
         const bool fix = sum < zero;
         const F fm = fix ? one : zero;
-        const double fd = fix ? 1.0 : 0.0;
-        const double m13 = xflip(fd, S.x13), m23 = xflip(fd, S.x23);
-        S.s13 = fma(m23, S.s12, fma(m13, S.s11, S.s13));
-        S.s23 = fma(m23, S.s22, fma(m13, S.s21, S.s23));
-        S.s33 = fma(m23, S.s32, fma(m13, S.s31, S.s33));
+        S.fix(fix);
         c = rfma(fm, sum, c);
         f = rfma(fm, h + (b + b), f);
         g = rfma(fm, h + (a + a), g);
     }
     // shear 1: col2 += t col1                                        551-567
+    int ti;
     const F den = a + a;
     const F rden = rcp_seeded(den, active);
     {
-        const F t = shear_quot(a, h, den, rden);
-        const double ts = xflip(rwide(t), S.x12);
-        S.s12 = fma(ts, S.s11, S.s12); S.s22 = fma(ts, S.s21, S.s22); S.s32 = fma(ts, S.s31, S.s32);
+        const F t = shear_quot(a, h, den, rden, ti);
+        S.shear12(rwide(t), ti);
         const F temp = a * t;
         h += temp;
         b = rfma(h, t, b);
@@ -733,9 +814,8 @@ __device__ __forceinline__ void reduce_trip(F &a, F &b, F &c, F &f, F &g, F &h, 
     {
         const F den2 = b + b;
         const F rden2 = rcp_seeded(den2, active);
-        const F t = shear_quot(b, f, den2, rden2);
-        const double ts = xflip(rwide(t), S.x23);
-        S.s13 = fma(ts, S.s12, S.s13); S.s23 = fma(ts, S.s22, S.s23); S.s33 = fma(ts, S.s32, S.s33);
+        const F t = shear_quot(b, f, den2, rden2, ti);
+        S.shear23(rwide(t), ti);
         const F temp = b * t;
         f += temp;
         c = rfma(f, t, c);
@@ -744,9 +824,8 @@ __device__ __forceinline__ void reduce_trip(F &a, F &b, F &c, F &f, F &g, F &h, 
     }
     // shear 3: col3 += t col1 (a, hence 2a, is unchanged)             587-603
     {
-        const F t = shear_quot(a, g, den, rden);
-        const double ts = xflip(rwide(t), S.x13);
-        S.s13 = fma(ts, S.s11, S.s13); S.s23 = fma(ts, S.s21, S.s23); S.s33 = fma(ts, S.s31, S.s33);
+        const F t = shear_quot(a, g, den, rden, ti);
+        S.shear13(rwide(t), ti);
         const F temp = a * t;
         g += temp;
         c = rfma(g, t, c);
@@ -754,30 +833,21 @@ __device__ __forceinline__ void reduce_trip(F &a, F &b, F &c, F &f, F &g, F &h, 
         g += temp;
     }
     // sort a <= b <= c with the reference's tie-breaks                605-624
-    // (form pairs swap by select on the ALU pipe, isometry columns arithmetically on the FP64 pipe)
+    // (form pairs swap by select on the ALU pipe, isometry columns arithmetically: FP64 pipe for DIso, FMA pipe for IIso)
     {
         const bool p = active & ((a > b) | ((a == b) & (rabs(f) > rabs(g))));
-        const double m = p ? 1.0 : 0.0;
         rswap(p, a, b); rswap(p, f, g);
-        dswap_fma(m, S.s11, S.s12); dswap_fma(m, S.s21, S.s22); dswap_fma(m, S.s31, S.s32);
-        const u32 o23 = S.x23;                         // (c1,c2,c3) <- (-c2,-c1,-c3)
-        S.sg1 ^= p ? (S.x12 ^ SIGN) : 0u; S.x23 = p ? S.x13 : S.x23; S.x13 = p ? o23 : S.x13;
+        S.swap12(p);
     }
     {
         const bool p = active & ((b > c) | ((b == c) & (rabs(g) > rabs(h))));
-        const double m = p ? 1.0 : 0.0;
         rswap(p, b, c); rswap(p, g, h);
-        dswap_fma(m, S.s12, S.s13); dswap_fma(m, S.s22, S.s23); dswap_fma(m, S.s32, S.s33);
-        const u32 o12 = S.x12;                         // (c1,c2,c3) <- (-c1,-c3,-c2)
-        S.sg1 ^= p ? SIGN : 0u; S.x12 = p ? S.x13 : S.x12; S.x13 = p ? o12 : S.x13;
+        S.swap23(p);
     }
     {
         const bool p = active & ((a > b) | ((a == b) & (rabs(f) > rabs(g))));
-        const double m = p ? 1.0 : 0.0;
         rswap(p, a, b); rswap(p, f, g);
-        dswap_fma(m, S.s11, S.s12); dswap_fma(m, S.s21, S.s22); dswap_fma(m, S.s31, S.s32);
-        const u32 o23 = S.x23;
-        S.sg1 ^= p ? (S.x12 ^ SIGN) : 0u; S.x23 = p ? S.x13 : S.x23; S.x13 = p ? o23 : S.x13;
+        S.swap12(p);
     }
     // sign normalisation                                              626-687
     // Restated: if f g h > 0 (all nonzero, evenly many negative) flip the negative ones;
@@ -794,7 +864,7 @@ __device__ __forceinline__ void reduce_trip(F &a, F &b, F &c, F &f, F &g, F &h, 
         const bool f3 = (caseA ? hneg : hpos) | (oddB & !fz & !gz & hz);
         const u32 n1 = f1 ? SIGN : 0u, n2 = f2 ? SIGN : 0u, n3 = f3 ? SIGN : 0u;
         f = rflip(f, n1); g = rflip(g, n2); h = rflip(h, n3);
-        S.sg1 ^= n1; S.x12 ^= n1 ^ n2; S.x23 ^= n2 ^ n3; S.x13 ^= n1 ^ n3;
+        S.negate(n1, n2, n3);
     }
     // exit test                                                       689-690
     sum = (((a + b) + f) + g) + h;
@@ -836,18 +906,17 @@ __device__ __forceinline__ bool boundary_fixup_fires(F a, F b, F c, F f, F g, F 
 // Returns the trip count; on_boundary says whether some fix-up of QuadForm.h:693-764 fires.
 struct DReduce {
     double a, b, c, f, g, h;
-    double s11, s12, s13, s21, s22, s23, s31, s32, s33;
+    double s[9];                  // in: the neighbor isometry, row-major; out (DIso): the reduced one
+    int si[9];                    // out (IIso): the reduced isometry
     bool on_boundary;
 };
 
-__device__ __forceinline__ int reduce_loop_fp64(DReduce &d, bool f32_tail)
+template <class ISO>
+__device__ __forceinline__ int reduce_loop(DReduce &d, bool f32_tail, ISO &S)
 {
     const unsigned warp = 0xffffffffu;
     double a = d.a, b = d.b, c = d.c, f = d.f, g = d.g, h = d.h;
-    DIso S;
-    S.s11 = d.s11; S.s12 = d.s12; S.s13 = d.s13; S.s21 = d.s21; S.s22 = d.s22; S.s23 = d.s23;
-    S.s31 = d.s31; S.s32 = d.s32; S.s33 = d.s33;
-    S.sg1 = S.x12 = S.x23 = S.x13 = 0u;
+    S.load(d.s);
     bool active = true;
     int iters = 0;
     double sum = (((a + b) + f) + g) + h;
@@ -878,10 +947,26 @@ __device__ __forceinline__ int reduce_loop_fp64(DReduce &d, bool f32_tail)
         d.on_boundary = boundary_fixup_fires(a, b, c, f, g, h);
         d.a = a; d.b = b; d.c = c; d.f = f; d.g = g; d.h = h;
     }
+    return iters;
+}
+
+// iso_int: the isometry runs in int32 ring arithmetic (PrimeCtx::iso32) and comes back in d.si
+__device__ __forceinline__ int reduce_loop_fp64(DReduce &d, bool f32_tail, bool iso_int = false)
+{
+    if (iso_int)
+    {
+        IIso S;
+        const int iters = reduce_loop(d, f32_tail, S);
+        d.si[0] = S.s11; d.si[1] = S.s12; d.si[2] = S.s13; d.si[3] = S.s21; d.si[4] = S.s22; d.si[5] = S.s23;
+        d.si[6] = S.s31; d.si[7] = S.s32; d.si[8] = S.s33;
+        return iters;
+    }
+    DIso S;
+    const int iters = reduce_loop(d, f32_tail, S);
     const u32 sg2 = S.sg1 ^ S.x12, sg3 = S.sg1 ^ S.x13;
-    d.s11 = xflip(S.s11, S.sg1); d.s21 = xflip(S.s21, S.sg1); d.s31 = xflip(S.s31, S.sg1);
-    d.s12 = xflip(S.s12, sg2); d.s22 = xflip(S.s22, sg2); d.s32 = xflip(S.s32, sg2);
-    d.s13 = xflip(S.s13, sg3); d.s23 = xflip(S.s23, sg3); d.s33 = xflip(S.s33, sg3);
+    d.s[0] = xflip(S.s11, S.sg1); d.s[3] = xflip(S.s21, S.sg1); d.s[6] = xflip(S.s31, S.sg1);
+    d.s[1] = xflip(S.s12, sg2); d.s[4] = xflip(S.s22, sg2); d.s[7] = xflip(S.s32, sg2);
+    d.s[2] = xflip(S.s13, sg3); d.s[5] = xflip(S.s23, sg3); d.s[8] = xflip(S.s33, sg3);
     return iters;
 }
 
@@ -949,19 +1034,28 @@ __device__ __forceinline__ bool reduce_prepare(Form<Z> &q, Iso<Z> &s, bool fp64_
     else if (!fp64_allowed) { ok = reduce_out_of_line(q, s); return false; }
     d.a = __ll2double_rn(q.a.low64()); d.b = __ll2double_rn(q.b.low64()); d.c = __ll2double_rn(q.c.low64());
     d.f = __ll2double_rn(q.f.low64()); d.g = __ll2double_rn(q.g.low64()); d.h = __ll2double_rn(q.h.low64());
-    d.s11 = __ll2double_rn(s.a11.low64()); d.s12 = __ll2double_rn(s.a12.low64()); d.s13 = __ll2double_rn(s.a13.low64());
-    d.s21 = __ll2double_rn(s.a21.low64()); d.s22 = __ll2double_rn(s.a22.low64()); d.s23 = __ll2double_rn(s.a23.low64());
-    d.s31 = __ll2double_rn(s.a31.low64()); d.s32 = __ll2double_rn(s.a32.low64()); d.s33 = __ll2double_rn(s.a33.low64());
+    d.s[0] = __ll2double_rn(s.a11.low64()); d.s[1] = __ll2double_rn(s.a12.low64()); d.s[2] = __ll2double_rn(s.a13.low64());
+    d.s[3] = __ll2double_rn(s.a21.low64()); d.s[4] = __ll2double_rn(s.a22.low64()); d.s[5] = __ll2double_rn(s.a23.low64());
+    d.s[6] = __ll2double_rn(s.a31.low64()); d.s[7] = __ll2double_rn(s.a32.low64()); d.s[8] = __ll2double_rn(s.a33.low64());
     return true;
 }
 template <class Z>
-__device__ __forceinline__ void reduce_finish(const DReduce &d, Form<Z> &q, Iso<Z> &s)
+__device__ __forceinline__ void reduce_finish(const DReduce &d, Form<Z> &q, Iso<Z> &s, bool iso_int = false)
 {
     q.a = Z(__double2ll_rn(d.a)); q.b = Z(__double2ll_rn(d.b)); q.c = Z(__double2ll_rn(d.c));
     q.f = Z(__double2ll_rn(d.f)); q.g = Z(__double2ll_rn(d.g)); q.h = Z(__double2ll_rn(d.h));
-    s.a11 = Z(__double2ll_rn(d.s11)); s.a12 = Z(__double2ll_rn(d.s12)); s.a13 = Z(__double2ll_rn(d.s13));
-    s.a21 = Z(__double2ll_rn(d.s21)); s.a22 = Z(__double2ll_rn(d.s22)); s.a23 = Z(__double2ll_rn(d.s23));
-    s.a31 = Z(__double2ll_rn(d.s31)); s.a32 = Z(__double2ll_rn(d.s32)); s.a33 = Z(__double2ll_rn(d.s33));
+    if (iso_int)
+    {
+        s.a11 = Z((i64)d.si[0]); s.a12 = Z((i64)d.si[1]); s.a13 = Z((i64)d.si[2]);
+        s.a21 = Z((i64)d.si[3]); s.a22 = Z((i64)d.si[4]); s.a23 = Z((i64)d.si[5]);
+        s.a31 = Z((i64)d.si[6]); s.a32 = Z((i64)d.si[7]); s.a33 = Z((i64)d.si[8]);
+    }
+    else
+    {
+        s.a11 = Z(__double2ll_rn(d.s[0])); s.a12 = Z(__double2ll_rn(d.s[1])); s.a13 = Z(__double2ll_rn(d.s[2]));
+        s.a21 = Z(__double2ll_rn(d.s[3])); s.a22 = Z(__double2ll_rn(d.s[4])); s.a23 = Z(__double2ll_rn(d.s[5]));
+        s.a31 = Z(__double2ll_rn(d.s[6])); s.a32 = Z(__double2ll_rn(d.s[7])); s.a33 = Z(__double2ll_rn(d.s[8]));
+    }
     if (d.on_boundary)
     {
         Form<Z> tq = q;          // copies: only these are address-taken by the out-of-line call
@@ -1257,9 +1351,9 @@ __device__ __forceinline__ bool fast_setup(const i64 *cur, const RepPrime &rp, u
     d.g = fma(2.0, temp2, gg);
     d.h = exact_div(hi_h, lo_h, hh1, P, iP);
     // isometry: [[u, 0, -1], [v, 1, 0], [1, 0, 0]], col2 += s1 col3, col1 += s2 col3, col2 *= p, col3 *= p^2
-    d.s11 = u - s2; d.s12 = -s1 * P; d.s13 = -PP;
-    d.s21 = v;      d.s22 = P;       d.s23 = 0.0;
-    d.s31 = 1.0;    d.s32 = 0.0;     d.s33 = 0.0;
+    d.s[0] = u - s2; d.s[1] = -s1 * P; d.s[2] = -PP;
+    d.s[3] = v;      d.s[4] = P;       d.s[5] = 0.0;
+    d.s[6] = 1.0;    d.s[7] = 0.0;     d.s[8] = 0.0;
     return generic;
 }
 
@@ -1362,8 +1456,11 @@ __device__ __forceinline__ int one_neighbor(int n, u32 t, const RepPrime &rp, co
     }
     if (in_fp64)                                             // warp-uniform
     {
-        if (reduce_loop_fp64(d, pc.f32_tail != 0) > TB_REDUCE_CAP) status = NBR_OVERFLOW;
-        reduce_finish(d, o.q, o.s);
+        // the isometry in int32 ring arithmetic when its final entries are proven below 2^31 -- but the neighbor's
+        // starting entries must convert too (below 2^31: p^2 <= 2^30 covers -p^2, s1 p and u - s2)
+        const bool iso_int = pc.iso32 != 0 && pc.p < 32768u;
+        if (reduce_loop_fp64(d, pc.f32_tail != 0, iso_int) > TB_REDUCE_CAP) status = NBR_OVERFLOW;
+        reduce_finish(d, o.q, o.s, iso_int);
     }
 
     int r = genus_lookup(o.q, gc);                           // Genus.h:575
