@@ -434,15 +434,17 @@ def test_row_kernel_global_scratch_walks_rows(tables, port_oracle, monkeypatch, 
 
 
 @pytest.mark.parametrize("name,p", [("85085", 101), ("1062347", 1009), ("1009091", 107), ("11", 65521), ("85085", 9973), ("11", 7)])
-@pytest.mark.parametrize("env", [None, "TBIRCH_NO_F32_TAIL", "TBIRCH_NO_PROVEN_BOUNDS"])
+@pytest.mark.parametrize("env", [None, "TBIRCH_NO_F32_TAIL", "TBIRCH_NO_ISO32", "TBIRCH_NO_FAST_SETUP", "TBIRCH_NO_PROVEN_BOUNDS"])
 def test_reduce_loop_forms(tables, port_oracle, monkeypatch, name, p, env):
-    """The reduce loop has three exact forms chosen per launch from host-proven bounds: binary64 form +
-    int32 ring isometry with a binary32 tail (reduce_loop_mixed, the default wherever the bounds hold),
-    the same without the tail (TBIRCH_NO_F32_TAIL), and the all-binary64 loop (reduce_loop_fp64,
-    TBIRCH_NO_PROVEN_BOUNDS).  Each must reproduce the oracle's reduced forms AND isometries
-    (neighbor records), matrices and isometry stream, in both integer modes."""
+    """Setup and reduce loop have several exact forms chosen per launch from host-proven bounds: the
+    neighbor set up in binary64 on the generic lane (fast_setup) or in integers on every lane
+    (TBIRCH_NO_FAST_SETUP); the loop's form part in binary64 with a binary32 tail or binary64 to the end
+    (TBIRCH_NO_F32_TAIL); its isometry in int32 ring arithmetic or in binary64 with lazy signs
+    (TBIRCH_NO_ISO32); per-lane magnitude tests instead of proven bounds (TBIRCH_NO_PROVEN_BOUNDS).
+    Each must reproduce the oracle's reduced forms AND isometries (neighbor records), matrices and
+    isometry stream, in both integer modes."""
     from ternary_birch_b200 import Genus, IsometrySequence
-    for v in ("TBIRCH_NO_F32_TAIL", "TBIRCH_NO_PROVEN_BOUNDS"):
+    for v in ("TBIRCH_NO_F32_TAIL", "TBIRCH_NO_ISO32", "TBIRCH_NO_FAST_SETUP", "TBIRCH_NO_PROVEN_BOUNDS"):
         monkeypatch.delenv(v, raising=False)
     if env:
         monkeypatch.setenv(env, "1")
