@@ -349,8 +349,6 @@ def main():
     copy_stream = torch.cuda.Stream(device=dev)
     pending = [None, None]                               # (HeckeResult, event) per buffer set
 
-    step_d2h = []                                        # bytes each step sends over PCIe: tells the read-back format it used
-
     def drain(slot):
         if pending[slot] is not None:
             res, ev = pending[slot]
@@ -373,7 +371,6 @@ def main():
         ev = torch.cuda.Event()
         ev.record(copy_stream)
         pending[slot] = (res, ev)
-        step_d2h.append(sum(res.transfer_bytes(k) for k in range(C)))
 
     # warm-up: W untimed steps, at least eight: both pinned result sets must have been written by the host
     # once (the first CPU store to a page of a fresh cudaHostAlloc mapping takes a minor fault), and the library
@@ -385,11 +382,7 @@ def main():
         step_e2e(i)
     drain(0)
     drain(1)
-    # the warm-up ran under the real concurrency: keep the read-back format each rank settled on (a pipeline
-    # restart like the one above perturbs the per-rank rate measurements and the ranks flap for ~10 steps)
-    frozen_format = L.tb_readback_freeze(1)
     sync_all()
-    del step_d2h[:]
     e_start = torch.cuda.Event(enable_timing=True)
     e_stop = torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
@@ -409,14 +402,11 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total_neighbors / (float(t.item()) * 1e-3)
-    L.tb_readback_freeze(0)
     my_steps = [round((b - a) * 1e3, 1) for a, b in zip(step_marks, step_marks[1:])]
     pol = [ctypes.c_double(), ctypes.c_double(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()]
     cabi.check(L.tb_readback_stats(*[ctypes.byref(x) for x in pol]))
     my_policy = dict(rank=rank, format="narrow" if pol[4].value else "plain", plain_gbs=round(pol[0].value, 1),
-                     narrow_gbs=round(pol[1].value, 1), plain_samples=pol[2].value, narrow_samples=pol[3].value,
-                     frozen_for_timed_steps="narrow" if frozen_format else "plain",
-                     step_d2h_mb=[round(b / 1e6) for b in step_d2h])
+                     narrow_gbs=round(pol[1].value, 1), plain_samples=pol[2].value, narrow_samples=pol[3].value)
 
     # ---- what can this host ingest?  All ranks at once: plain DMA into pinned memory, then the
     # widening threads alone (profiles/r2a_d2h_probe_n4.md explains why these are the two ceilings).

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TBIRCH_ABI_VERSION 3
+#define TBIRCH_ABI_VERSION 2
 
 typedef enum tb_status {
     TB_OK = 0,
@@ -142,11 +142,6 @@ int64_t tb_hecke_transfer_bytes(const tb_hecke *h, int64_t k);
  * (0 plain, 1 narrow).  TBIRCH_NO_NARROW_COPY / TBIRCH_FORCE_NARROW_COPY pin the choice. */
 int tb_readback_stats(double *plain_gbps, double *narrow_gbps, int *plain_samples, int *narrow_samples,
                       int *current);
-/* on != 0: keep the format currently preferred on this device (no switching, no probes of the other
- * one) until called with 0 -- a caller that has warmed up under its real concurrency (several ranks
- * per host adapt against each other, and every pipeline restart perturbs their measurements) pins
- * the settled choice for its steady state.  Returns the format in force (0 plain, 1 narrow). */
-int tb_readback_freeze(int on);
 /* Host-side widening throughput of this machine (no GPU involved; diagnostic): output GB/s of the
  * library's thread pool on `entries` packed entries, the pool size, and whether the AVX2
  * streaming-store path is in use. */

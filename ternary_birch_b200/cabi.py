@@ -51,8 +51,6 @@ def lib() -> ctypes.CDLL:
     L.tb_hecke_transfer_bytes.restype = i64
     L.tb_host_widen_probe.argtypes = [i64, vp, vp, vp]
     L.tb_readback_stats.argtypes = [vp, vp, vp, vp, vp]
-    L.tb_readback_freeze.argtypes = [ctypes.c_int]
-    L.tb_readback_freeze.restype = ctypes.c_int
     L.tb_hecke_packed_bytes.argtypes = [vp, vp]
     L.tb_hecke_packed_bytes.restype = i64
     L.tb_hecke_pack.argtypes = [vp, vp, vp]
@@ -107,7 +105,7 @@ def lib() -> ctypes.CDLL:
     L.tb_table_desc.argtypes = [vp, ctypes.POINTER(GenusDesc), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
     L.tb_table_destroy.argtypes = [vp]
     L.tb_table_destroy.restype = None
-    if L.tb_abi_version() != 3:
+    if L.tb_abi_version() != 2:
         raise RuntimeError("libtbirch.so ABI version mismatch")
     _lib = L
     return L
@@ -119,7 +117,7 @@ EXPORTS = [
     "tb_genus_num_conductors", "tb_genus_conductor", "tb_genus_dim",
     "tb_hecke_compute", "tb_hecke_compute_rows", "tb_hecke_num_conductors", "tb_hecke_conductor",
     "tb_hecke_dim", "tb_hecke_rows", "tb_hecke_row_begin", "tb_hecke_nnz", "tb_hecke_copy_sparse",
-    "tb_hecke_copy_sparse_async", "tb_hecke_copy_sparse_all", "tb_hecke_copy_wait", "tb_hecke_transfer_bytes", "tb_host_widen_probe", "tb_readback_stats", "tb_readback_freeze", "tb_hecke_packed_bytes", "tb_hecke_pack", "tb_unpack_rows",
+    "tb_hecke_copy_sparse_async", "tb_hecke_copy_sparse_all", "tb_hecke_copy_wait", "tb_hecke_transfer_bytes", "tb_host_widen_probe", "tb_readback_stats", "tb_hecke_packed_bytes", "tb_hecke_pack", "tb_unpack_rows",
     "tb_hecke_copy_dense", "tb_hecke_destroy", "tb_eigenvalues", "tb_isoseq_open", "tb_isoseq_done",
     "tb_isoseq_next", "tb_isoseq_read", "tb_isoseq_close", "tb_neighbor_records", "tb_int_peak", "tb_int_peak_detail",
     "tb_quad_form", "tb_genus_enumerate", "tb_table_desc", "tb_table_destroy",

@@ -656,15 +656,6 @@ extern "C" int tb_readback_stats(double *plain_gbps, double *narrow_gbps, int *p
     return TB_OK;
 }
 
-extern "C" int tb_readback_freeze(int on)
-{
-    ReadbackPolicy &pol = readback_policy();
-    std::lock_guard<std::mutex> lk(pol.mx);
-    pol.frozen = on != 0;
-    if (!pol.frozen) { pol.since_probe = 0; pol.pending_probe = 0; }
-    return pol.current;
-}
-
 // ---------------------------------------------------------------------------
 // Final integer gather of the Hecke rows: the one exchange of the multi-GPU path.
 // Each rank packs ALL conductors of its tb_hecke into one contiguous device buffer in the

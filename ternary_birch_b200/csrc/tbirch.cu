@@ -265,12 +265,10 @@ struct ReadbackPolicy {
     int current = NARROW;
     int since_probe = 0;              // read-backs measured since the other format was last tried
     int pending_probe = 0;            // a probe of the other format has been handed out and not measured yet
-    bool frozen = false;              // tb_readback_freeze: `current` is kept, nothing is probed
 
     int choose()
     {
         std::lock_guard<std::mutex> lk(mx);
-        if (frozen) return current;
         if (samples[NARROW] == 0) return NARROW;          // one measured read-back of each format first
         if (samples[PLAIN] == 0) return PLAIN;
         if (rate[1 - current] > 1.15 * rate[current]) current = 1 - current;   // hysteresis: ranks adapt concurrently

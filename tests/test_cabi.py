@@ -33,7 +33,7 @@ def test_exports_match_header(built):
     for name in names:
         assert hasattr(L, name), f"libtbirch.so does not export {name}"
     assert sorted(built.EXPORTS) == names
-    assert L.tb_abi_version() == 3
+    assert L.tb_abi_version() == 2
 
 
 @pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
