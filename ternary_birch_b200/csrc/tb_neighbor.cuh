@@ -736,8 +736,8 @@ struct DIso {
 // that every entry of the isometry the loop ENDS with is below 2^31 in magnitude, hence the wrapped
 // result is the result, whatever the intermediates did.  That takes 42 of the 115 FP64-pipe
 // instructions of a binary64 trip (the pipe that stage saturates) to IMAD on the otherwise idle FMA
-// pipe, halves the isometry's registers and needs no lazy signs: a conditional swap-and-negate of
-// columns i, j is  u = c_i + c_j; c_i -= m u; c_j -= m u  with m = 1 or 0.
+// pipe, halves the isometry's registers and needs no lazy signs: swaps, negations and the fix step are
+// predicated integer moves and adds.
 struct IIso {
     int s11, s12, s13, s21, s22, s23, s31, s32, s33;
 
@@ -749,26 +749,23 @@ struct IIso {
     }
     __device__ __forceinline__ void fix(bool on)
     {
-        const int fi = on ? 1 : 0;
-        s13 += fi * (s11 + s12); s23 += fi * (s21 + s22); s33 += fi * (s31 + s32);
+        s13 = on ? s13 + s11 + s12 : s13; s23 = on ? s23 + s21 + s22 : s23; s33 = on ? s33 + s31 + s32 : s33;
     }
     __device__ __forceinline__ void shear12(double, int t) { s12 += t * s11; s22 += t * s21; s32 += t * s31; }
     __device__ __forceinline__ void shear23(double, int t) { s13 += t * s12; s23 += t * s22; s33 += t * s32; }
     __device__ __forceinline__ void shear13(double, int t) { s13 += t * s11; s23 += t * s21; s33 += t * s31; }
-    static __device__ __forceinline__ void swapneg(int m, int nu, int &ci, int &cj, int &ck)
+    static __device__ __forceinline__ void swapneg(bool p, int &ci, int &cj, int &ck)
     {
-        const int u = ci + cj;
-        ci -= m * u; cj -= m * u; ck *= nu;
+        const int ni = -ci, nj = -cj, nk = -ck;
+        ci = p ? nj : ci; cj = p ? ni : cj; ck = p ? nk : ck;
     }
     __device__ __forceinline__ void swap12(bool p)
     {
-        const int m = p ? 1 : 0, nu = 1 - 2 * m;
-        swapneg(m, nu, s11, s12, s13); swapneg(m, nu, s21, s22, s23); swapneg(m, nu, s31, s32, s33);
+        swapneg(p, s11, s12, s13); swapneg(p, s21, s22, s23); swapneg(p, s31, s32, s33);
     }
     __device__ __forceinline__ void swap23(bool p)
     {
-        const int m = p ? 1 : 0, nu = 1 - 2 * m;
-        swapneg(m, nu, s12, s13, s11); swapneg(m, nu, s22, s23, s21); swapneg(m, nu, s32, s33, s31);
+        swapneg(p, s12, s13, s11); swapneg(p, s22, s23, s21); swapneg(p, s32, s33, s31);
     }
     __device__ __forceinline__ void negate(u32 n1, u32 n2, u32 n3)
     {
