@@ -656,8 +656,9 @@ __device__ __forceinline__ int rquot(double qm) { return __double2loint(qm); }  
 __device__ __forceinline__ int rquot(float qm) { return __float_as_int(qm) - 0x4B400000; }
 __device__ __forceinline__ double rcorr(double, int m) { return __hiloint2double(m & (int)0xBFF00000, 0); }   // -1.0 or 0.0
 __device__ __forceinline__ float rcorr(float, int m) { return __int_as_float(m & (int)0xBF800000); }
-__device__ __forceinline__ double rflip(double x, u32 m) { return xflip(x, m); }
-__device__ __forceinline__ float rflip(float x, u32 m) { return __int_as_float(__float_as_int(x) ^ (int)m); }
+// -x if p else x: a sign-bit XOR in binary64 (ALU, off the FP64 pipe), a predicated negation in binary32
+__device__ __forceinline__ double rnegif(double x, bool p) { return xflip(x, p ? 0x80000000u : 0u); }
+__device__ __forceinline__ float rnegif(float x, bool p) { return p ? -x : x; }
 __device__ __forceinline__ double rabs(double x) { return fabs(x); }
 __device__ __forceinline__ float rabs(float x) { return fabsf(x); }
 __device__ __forceinline__ double rwide(double t) { return t; }
@@ -725,8 +726,9 @@ struct DIso {
         const u32 o12 = x12;
         sg1 ^= p ? 0x80000000u : 0u; x12 = p ? x13 : x12; x13 = p ? o12 : x13;
     }
-    __device__ __forceinline__ void negate(u32 n1, u32 n2, u32 n3)        // sign-bit masks of the columns to negate
+    __device__ __forceinline__ void negate(bool f1, bool f2, bool f3)    // which columns to negate
     {
+        const u32 n1 = f1 ? 0x80000000u : 0u, n2 = f2 ? 0x80000000u : 0u, n3 = f3 ? 0x80000000u : 0u;
         sg1 ^= n1; x12 ^= n1 ^ n2; x23 ^= n2 ^ n3; x13 ^= n1 ^ n3;
     }
 };
@@ -767,7 +769,7 @@ struct IIso {
     {
         swapneg(p, s12, s13, s11); swapneg(p, s22, s23, s21); swapneg(p, s32, s33, s31);
     }
-    __device__ __forceinline__ void negate(u32 n1, u32 n2, u32 n3)
+    __device__ __forceinline__ void negate(bool n1, bool n2, bool n3)
     {
         s11 = n1 ? -s11 : s11; s21 = n1 ? -s21 : s21; s31 = n1 ? -s31 : s31;
         s12 = n2 ? -s12 : s12; s22 = n2 ? -s22 : s22; s32 = n2 ? -s32 : s32;
@@ -782,7 +784,6 @@ template <class F, class ISO>
 __device__ __forceinline__ void reduce_trip(F &a, F &b, F &c, F &f, F &g, F &h, F &sum, ISO &S, bool &active)
 {
     const F zero = F(0), one = F(1);
-    const u32 SIGN = 0x80000000u;
     // a + b + f + g + h < 0                                          542-549
     // (some lane of nearly every trip needs it, so it runs unconditionally with a 0/1 multiplier
     //  instead of under a vote and a divergent branch)
@@ -859,9 +860,8 @@ __device__ __forceinline__ void reduce_trip(F &a, F &b, F &c, F &f, F &g, F &h, 
         const bool f1 = (caseA ? fneg : fpos) | (oddB & fz);
         const bool f2 = (caseA ? gneg : gpos) | (oddB & !fz & gz);
         const bool f3 = (caseA ? hneg : hpos) | (oddB & !fz & !gz & hz);
-        const u32 n1 = f1 ? SIGN : 0u, n2 = f2 ? SIGN : 0u, n3 = f3 ? SIGN : 0u;
-        f = rflip(f, n1); g = rflip(g, n2); h = rflip(h, n3);
-        S.negate(n1, n2, n3);
+        f = rnegif(f, f1); g = rnegif(g, f2); h = rnegif(h, f3);
+        S.negate(f1, f2, f3);
     }
     // exit test                                                       689-690
     sum = (((a + b) + f) + g) + h;
