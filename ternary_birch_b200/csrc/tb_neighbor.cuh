@@ -50,6 +50,7 @@ struct PrimeCtx {
     u64 pp;
     double pd, ppd;   // p, p^2
     double inv_pd, inv_ppd;   // RN(1 / p), RN(1 / p^2)
+    u64 pinv64;       // p^-1 mod 2^64 (odd p), else 0
     InvDiv dp;        // division by p
     InvDiv dpp;       // division by p^2
     const u32 *inv_lut;   // [p] inverses mod p, or nullptr
@@ -740,42 +741,64 @@ struct DIso {
 // instructions of a binary64 trip (the pipe that stage saturates) to IMAD on the otherwise idle FMA
 // pipe, halves the isometry's registers and needs no lazy signs: swaps, negations and the fix step are
 // predicated integer moves and adds.
+// Only rows 1 and 2 are carried: the rows of S are independent under column operations, and row 3 follows
+// from the other two at the end (recover_row3), which saves a third of the isometry's work in every trip.
 struct IIso {
-    int s11, s12, s13, s21, s22, s23, s31, s32, s33;
+    int s11, s12, s13, s21, s22, s23;
 
     __device__ __forceinline__ void load(const double *v)
     {
         s11 = __double2int_rn(v[0]); s12 = __double2int_rn(v[1]); s13 = __double2int_rn(v[2]);
         s21 = __double2int_rn(v[3]); s22 = __double2int_rn(v[4]); s23 = __double2int_rn(v[5]);
-        s31 = __double2int_rn(v[6]); s32 = __double2int_rn(v[7]); s33 = __double2int_rn(v[8]);
     }
     __device__ __forceinline__ void fix(bool on)
     {
-        s13 = on ? s13 + s11 + s12 : s13; s23 = on ? s23 + s21 + s22 : s23; s33 = on ? s33 + s31 + s32 : s33;
+        s13 = on ? s13 + s11 + s12 : s13; s23 = on ? s23 + s21 + s22 : s23;
     }
-    __device__ __forceinline__ void shear12(double, int t) { s12 += t * s11; s22 += t * s21; s32 += t * s31; }
-    __device__ __forceinline__ void shear23(double, int t) { s13 += t * s12; s23 += t * s22; s33 += t * s32; }
-    __device__ __forceinline__ void shear13(double, int t) { s13 += t * s11; s23 += t * s21; s33 += t * s31; }
+    __device__ __forceinline__ void shear12(double, int t) { s12 += t * s11; s22 += t * s21; }
+    __device__ __forceinline__ void shear23(double, int t) { s13 += t * s12; s23 += t * s22; }
+    __device__ __forceinline__ void shear13(double, int t) { s13 += t * s11; s23 += t * s21; }
     static __device__ __forceinline__ void swapneg(bool p, int &ci, int &cj, int &ck)
     {
         const int ni = -ci, nj = -cj, nk = -ck;
         ci = p ? nj : ci; cj = p ? ni : cj; ck = p ? nk : ck;
     }
-    __device__ __forceinline__ void swap12(bool p)
-    {
-        swapneg(p, s11, s12, s13); swapneg(p, s21, s22, s23); swapneg(p, s31, s32, s33);
-    }
-    __device__ __forceinline__ void swap23(bool p)
-    {
-        swapneg(p, s12, s13, s11); swapneg(p, s22, s23, s21); swapneg(p, s32, s33, s31);
-    }
+    __device__ __forceinline__ void swap12(bool p) { swapneg(p, s11, s12, s13); swapneg(p, s21, s22, s23); }
+    __device__ __forceinline__ void swap23(bool p) { swapneg(p, s12, s13, s11); swapneg(p, s22, s23, s21); }
     __device__ __forceinline__ void negate(bool n1, bool n2, bool n3)
     {
-        s11 = n1 ? -s11 : s11; s21 = n1 ? -s21 : s21; s31 = n1 ? -s31 : s31;
-        s12 = n2 ? -s12 : s12; s22 = n2 ? -s22 : s22; s32 = n2 ? -s32 : s32;
-        s13 = n3 ? -s13 : s13; s23 = n3 ? -s23 : s23; s33 = n3 ? -s33 : s33;
+        s11 = n1 ? -s11 : s11; s21 = n1 ? -s21 : s21;
+        s12 = n2 ? -s12 : s12; s22 = n2 ? -s22 : s22;
+        s13 = n3 ? -s13 : s13; s23 = n3 ? -s23 : s23;
     }
 };
+
+// Row 3 of the neighbor isometry S from rows r1, r2.  With G the Gram matrix of the representative
+// (2a h g / h 2b f / g f 2c) and G' that of the current form, S^T G S = p^2 G' and det S = +p^3 hold after
+// build_neighbor and are kept by every step of the reduction (shears, paired swap-negations, sign flips in
+// pairs), so cof(S) = p^3 S^-T and  p G S = cof(S) G'.  The third row of cof(S) is r1 x r2, hence
+//     2c r3 = (r1 x r2) G' / p - g r1 - f r2.
+// (r1 x r2) G' can exceed 64 bits, but it is p times an integer below 2^63, so it is formed modulo 2^64 and
+// divided exactly by multiplying with p^-1 mod 2^64; the rest is small (|2c r3| < 2^51 under iso32 and the
+// table bound) and the last division goes through binary64.
+__device__ __forceinline__ void recover_row3(const int *r, const i64 *cur, i64 qa, i64 qb, i64 qc, i64 qf, i64 qg, i64 qh,
+                                             u64 pinv, int *r3)
+{
+    const i64 s11 = r[0], s12 = r[1], s13 = r[2], s21 = r[3], s22 = r[4], s23 = r[5];
+    const u64 x1 = (u64)(s12 * s23 - s13 * s22), x2 = (u64)(s13 * s21 - s11 * s23), x3 = (u64)(s11 * s22 - s12 * s21);
+    const u64 A = (u64)qa, B = (u64)qb, C = (u64)qc, F = (u64)qf, G = (u64)qg, H = (u64)qh;
+    const u64 w1 = x1 * (A + A) + x2 * H + x3 * G;
+    const u64 w2 = x1 * H + x2 * (B + B) + x3 * F;
+    const u64 w3 = x1 * G + x2 * F + x3 * (C + C);
+    const i64 g0 = __ldg(cur + 4), f0 = __ldg(cur + 3), c0 = __ldg(cur + 2);
+    const i64 t1 = (i64)(w1 * pinv) - (g0 * s11 + f0 * s21);
+    const i64 t2 = (i64)(w2 * pinv) - (g0 * s12 + f0 * s22);
+    const i64 t3 = (i64)(w3 * pinv) - (g0 * s13 + f0 * s23);
+    const double inv = 1.0 / __ll2double_rn(c0 + c0);
+    r3[0] = __double2int_rn(__ll2double_rn(t1) * inv);
+    r3[1] = __double2int_rn(__ll2double_rn(t2) * inv);
+    r3[2] = __double2int_rn(__ll2double_rn(t3) * inv);
+}
 
 // One trip on every lane of the warp; finished lanes are frozen: their reciprocals (hence shear
 // quotients) and swap predicates are masked, the fix step and the sign normalisation cannot fire on
@@ -904,7 +927,7 @@ __device__ __forceinline__ bool boundary_fixup_fires(F a, F b, F c, F f, F g, F 
 struct DReduce {
     double a, b, c, f, g, h;
     double s[9];                  // in: the neighbor isometry, row-major; out (DIso): the reduced one
-    int si[9];                    // out (IIso): the reduced isometry
+    int si[6];                    // out (IIso): rows 1 and 2 of the reduced isometry
     bool on_boundary;
 };
 
@@ -955,8 +978,7 @@ __device__ __forceinline__ int reduce_loop_fp64(DReduce &d, bool f32_tail, bool 
         IIso S;
         const int iters = reduce_loop(d, f32_tail, S);
         d.si[0] = S.s11; d.si[1] = S.s12; d.si[2] = S.s13; d.si[3] = S.s21; d.si[4] = S.s22; d.si[5] = S.s23;
-        d.si[6] = S.s31; d.si[7] = S.s32; d.si[8] = S.s33;
-        return iters;
+        return iters;                                    // row 3: reduce_finish
     }
     DIso S;
     const int iters = reduce_loop(d, f32_tail, S);
@@ -1037,15 +1059,19 @@ __device__ __forceinline__ bool reduce_prepare(Form<Z> &q, Iso<Z> &s, bool fp64_
     return true;
 }
 template <class Z>
-__device__ __forceinline__ void reduce_finish(const DReduce &d, Form<Z> &q, Iso<Z> &s, bool iso_int = false)
+__device__ __forceinline__ void reduce_finish(const DReduce &d, Form<Z> &q, Iso<Z> &s, bool iso_int = false,
+                                              const i64 *cur = nullptr, u64 pinv = 0)
 {
-    q.a = Z(__double2ll_rn(d.a)); q.b = Z(__double2ll_rn(d.b)); q.c = Z(__double2ll_rn(d.c));
-    q.f = Z(__double2ll_rn(d.f)); q.g = Z(__double2ll_rn(d.g)); q.h = Z(__double2ll_rn(d.h));
+    const i64 qa = __double2ll_rn(d.a), qb = __double2ll_rn(d.b), qc = __double2ll_rn(d.c);
+    const i64 qf = __double2ll_rn(d.f), qg = __double2ll_rn(d.g), qh = __double2ll_rn(d.h);
+    q.a = Z(qa); q.b = Z(qb); q.c = Z(qc); q.f = Z(qf); q.g = Z(qg); q.h = Z(qh);
     if (iso_int)
     {
+        int r3[3];
+        recover_row3(d.si, cur, qa, qb, qc, qf, qg, qh, pinv, r3);
         s.a11 = Z((i64)d.si[0]); s.a12 = Z((i64)d.si[1]); s.a13 = Z((i64)d.si[2]);
         s.a21 = Z((i64)d.si[3]); s.a22 = Z((i64)d.si[4]); s.a23 = Z((i64)d.si[5]);
-        s.a31 = Z((i64)d.si[6]); s.a32 = Z((i64)d.si[7]); s.a33 = Z((i64)d.si[8]);
+        s.a31 = Z((i64)r3[0]); s.a32 = Z((i64)r3[1]); s.a33 = Z((i64)r3[2]);
     }
     else
     {
@@ -1455,9 +1481,9 @@ __device__ __forceinline__ int one_neighbor(int n, u32 t, const RepPrime &rp, co
     {
         // the isometry in int32 ring arithmetic when its final entries are proven below 2^31 -- but the neighbor's
         // starting entries must convert too (below 2^31: p^2 <= 2^30 covers -p^2, s1 p and u - s2)
-        const bool iso_int = pc.iso32 != 0 && pc.p < 32768u;
+        const bool iso_int = pc.iso32 != 0 && pc.p < 32768u && pc.pinv64 != 0;
         if (reduce_loop_fp64(d, pc.f32_tail != 0, iso_int) > TB_REDUCE_CAP) status = NBR_OVERFLOW;
-        reduce_finish(d, o.q, o.s, iso_int);
+        reduce_finish(d, o.q, o.s, iso_int, cur, pc.pinv64);
     }
 
     int r = genus_lookup(o.q, gc);                           // Genus.h:575

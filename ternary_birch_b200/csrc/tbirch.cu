@@ -729,6 +729,9 @@ static int setup_prime(tb_genus *g, uint64_t p)
         // aa + s2 (gg + cc s2) <= B p^2 + p^2 (B (3p/2 + 1) + Bmid p^2) with |s2| < p^2 and cc = a <= Bmid
         pc.pd = (double)p; pc.ppd = (double)(p * p);
         pc.inv_pd = 1.0 / pc.pd; pc.inv_ppd = 1.0 / pc.ppd;
+        // p^-1 mod 2^64 (Newton) for recover_row3; it also needs 2c r3 and G31 r1 + G32 r2 + G33 r3 exact in
+        // binary64 resp. int64: |r| < 2^31 (iso32) and table coefficients below 2^20
+        if ((p & 1) && g->log2_coef < 20) { u64 x = p; for (int it = 0; it < 6; ++it) x *= 2 - p * x; pc.pinv64 = x; }
         if (pc.m32 && pc.use_lut && pc.proven_small && pc.fp64_reduce)
         {
             const unsigned __int128 B = (unsigned __int128)ceil(exp2(g->log2_coef)) + 1, Bm = (unsigned __int128)ceil(exp2(g->log2_mid)) + 1;
