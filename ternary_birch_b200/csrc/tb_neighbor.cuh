@@ -3,11 +3,15 @@
 // Device-side building blocks of the hot path:
 //   line_for_t        t -> isotropic line mod p      NeighborManager.h:50-144, 370-394
 //   build_neighbor    lattice + isometry             NeighborManager.h:207-356
-//   eisenstein_reduce unique reduced representative  QuadForm.h:530-767
+//   fast_setup        both of the above in binary64 on the generic lane, under host-proven bounds
+//   eisenstein_reduce unique reduced representative  QuadForm.h:530-767   (the literal integer loop)
+//   reduce_loop       the same loop, exact in binary64 then binary32; isometry as DIso or IIso
+//   reduce_boundary   post-loop fix-ups              QuadForm.h:693-764
 //   genus_lookup      open-addressing probe          HashMap.h:68-89, QuadForm.cpp:779-803
 //   spinor_norm       spinor/Kronecker class         Spinor.h:19-66, Genus.h:582-615
-// One thread owns one neighbor.  All of it is templated on the integer mode Z
-// (W64 | C128 | U128, tb_int.cuh).
+//   one_neighbor      the loop body of Genus.h:567-618
+// One thread owns one neighbor.  The integer code is templated on the integer mode Z
+// (W64 | X64 | C128 | U128, tb_int.cuh).
 #pragma once
 
 #include "tb_int.cuh"
@@ -567,7 +571,7 @@ __device__ __noinline__ bool eisenstein_reduce(Form<Z> &q, Iso<Z> &s)
 }
 
 // ---------------------------------------------------------------------------
-// FP64 fast path of the same reduction (both integer modes).
+// Floating-point form of the same reduction (all integer modes): reduce_trip / reduce_loop below.
 //
 // B200's FP64 pipe issues DFMA/DADD/DSETP at the same rate as each integer pipe
 // and is otherwise idle in this kernel, while 64-bit integer compares, selects
@@ -575,14 +579,18 @@ __device__ __noinline__ bool eisenstein_reduce(Form<Z> &q, Iso<Z> &s)
 // an integer, so it is computed EXACTLY in binary64 as long as it stays below
 // 2^53: a multiply-add is one DFMA (the product is never rounded separately), a
 // compare one DSETP (|x| is a free operand modifier), a sign flip one LOP3.
+// Once the coefficients are below 2^20 the form part continues in binary32 (see
+// "Binary32 tail" further down); the isometry is carried in binary64 with lazy
+// signs (DIso) or, under a host-proven bound, in int32 ring arithmetic (IIso).
 //
 // Why the values stay small (positive definite form, exact arithmetic):
 //   * diagonal coefficients are values Q(v) of the current basis vectors; each
 //     shear replaces one by a not-larger value, swaps permute them and the
 //     "sum < 0" step replaces c by Q(1,1,1) < c: they never grow;
 //   * off-diagonals obey f^2 < 4bc, g^2 < 4ac, h^2 < 4ab, so |f|,|g|,|h| < 2 max(a,b,c);
-//   * a shear's intermediates are a t (|t| <= (|h|+a)/2a + 1), h + a t, and DFMA
-//     results that are themselves new coefficients: all below 5 max(a,b,c);
+//   * a shear's intermediates are a t (|t| <= (|h|+a)/2a + 1, so |a t| <= 2.5 max), h + a t (<= 4.5 max)
+//     and FMA results that are themselves new coefficients; the fix step forms h + 2b (< 4 max) and
+//     the running sum a + b + f + g + h stays below 8 max(a,b,c);
 //   * isometry columns are lattice vectors v with Q_rep(v) = p^2 * (diagonal
 //     coefficient), so |v_i| <= p sqrt(max(a,b,c) / lambda_min(Q_rep)); the host
 //     enables this path only when that bound is below 2^52 (PrimeCtx::fp64_reduce).
@@ -590,11 +598,10 @@ __device__ __noinline__ bool eisenstein_reduce(Form<Z> &q, Iso<Z> &s)
 // magnitude (warp vote); otherwise the warp takes the integer loop above.
 //
 // SIMT shape: the body is branch-free (shears with t = 0 are no-ops, swaps and
-// sign flips are selects), so a warp diverges only on the trip count; finished
-// lanes are frozen by masking their quotients and predicates.  Column negations
-// of the isometry are three lazy sign bits folded into the shear multipliers.
-// The operation order is the reference's (QuadForm.h:540-691), so the isometry
-// is bit-identical.
+// sign flips are selects or predicated moves), so a warp diverges only on the
+// trip count; finished lanes are frozen by zeroing their reciprocal seeds (all
+// three quotients become 0) and masking the swap predicates.  The operation order
+// is the reference's (QuadForm.h:540-691), so the isometry is bit-identical.
 // ---------------------------------------------------------------------------
 // 1 / d to ~2^-36 relative: the hardware's ~20-bit seed and ONE Newton step.  That is all the shear
 // quotients need: on a positive definite form |h| < 2 sqrt(ab), |f| < 2 sqrt(bc), |g| < 2 sqrt(ac), so
