@@ -61,3 +61,47 @@ def test_prime_and_row_shards_cover_everything():
         blocks = shard.row_shards(10316, world)
         assert blocks[0][0] == 0 and blocks[-1][1] == 10316
         assert all(a[1] == b[0] for a, b in zip(blocks[:-1], blocks[1:]))
+
+
+@pytest.mark.parametrize("name,p", [("85085", 101), ("85085", 3), ("1062347", 29), ("11", 97)])      # primes not dividing the level
+def test_isometry_third_row_identity(tables, port_oracle, name, p):
+    """The algebra behind recover_row3 (csrc/tb_neighbor.cuh), checked on the oracle's neighbor records with
+    exact integers: for a neighbor isometry S of representative Q with reduced form Q', S^T G S = p^2 G' and
+    det S = +p^3, hence p G S = cof(S) G' and the third row of S follows from the other two,
+        2c r3 = (r1 x r2) G' / p - g r1 - f r2,
+    where (r1 x r2) G' is formed modulo 2^64 and divided by p through p^-1 mod 2^64 -- as the kernel does."""
+    t = tables(name)
+    rec = port_oracle(name).neighbor_records(p, False)          # [N][p+1][20]: line, form, isometry, r, spin
+    mask = (1 << 64) - 1
+    pinv = pow(p, -1, 1 << 64)
+
+    def gram(q):
+        a, b, c, f, g, h = (int(x) for x in q)
+        return [[2 * a, h, g], [h, 2 * b, f], [g, f, 2 * c]]
+
+    def signed(x):
+        x &= mask
+        return x - (1 << 64) if x >> 63 else x
+
+    checked = 0
+    for n in range(min(t.N, 12)):
+        G = gram(t.q[n])
+        g0, f0, c0 = int(t.q[n][4]), int(t.q[n][3]), int(t.q[n][2])
+        for row in rec[n]:
+            Gp = gram(row[3:9])
+            S = [[int(row[9 + 3 * i + j]) for j in range(3)] for i in range(3)]
+            # S^T G S = p^2 G'
+            GS = [[sum(G[i][k] * S[k][j] for k in range(3)) for j in range(3)] for i in range(3)]
+            StGS = [[sum(S[k][i] * GS[k][j] for k in range(3)) for j in range(3)] for i in range(3)]
+            assert StGS == [[p * p * Gp[i][j] for j in range(3)] for i in range(3)]
+            det = (S[0][0] * (S[1][1] * S[2][2] - S[1][2] * S[2][1]) - S[0][1] * (S[1][0] * S[2][2] - S[1][2] * S[2][0])
+                   + S[0][2] * (S[1][0] * S[2][1] - S[1][1] * S[2][0]))
+            assert det == p ** 3
+            r1, r2 = S[0], S[1]
+            x = [r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]]
+            w = [sum(x[i] * Gp[i][j] for i in range(3)) & mask for j in range(3)]           # modulo 2^64
+            tt = [signed(w[j] * pinv) - (g0 * r1[j] + f0 * r2[j]) for j in range(3)]
+            assert all(v % (2 * c0) == 0 for v in tt)
+            assert [v // (2 * c0) for v in tt] == S[2]
+            checked += 1
+    assert checked >= 24
