@@ -105,3 +105,62 @@ def test_isometry_third_row_identity(tables, port_oracle, name, p):
             assert [v // (2 * c0) for v in tt] == S[2]
             checked += 1
     assert checked >= 24
+
+
+@pytest.mark.parametrize("name,p", [("85085", 101), ("1062347", 29), ("11", 997)])
+def test_fast_setup_closed_form(tables, port_oracle, name, p):
+    """The closed form fast_setup (csrc/tb_neighbor.cuh) computes on the generic lane -- line with z = 1, g' != 0
+    mod p: residues s1, s2 with the reference's truncate-then-shift rule, the neighbor's six coefficients with the
+    two exact divisions, and the isometry [[u - s2, -s1 p, -p^2], [v, p, 0], [1, 0, 0]] -- restated with exact
+    integers, reduced by the oracle's QuadForm::reduce and compared with the oracle's own neighbor records."""
+    import ctypes
+    t = tables(name)
+    po = port_oracle(name)
+    lib = po.lib
+    lib.tbo_isotropic_vector.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+    lib.tbo_reduce.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    rec = po.neighbor_records(p, False)
+    base = po.base_points(p)
+    pp, half = p * p, p >> 1
+    generic = 0
+    for n in range(min(t.N, 6)):
+        q = np.ascontiguousarray(t.q[n], dtype=np.int64)
+        b3 = np.ascontiguousarray(base[n], dtype=np.int64)
+        a, b, c, f, g, h = (int(x) for x in q)
+        vec = np.zeros(3, dtype=np.int64)
+        for tt in range(p + 1):
+            lib.tbo_isotropic_vector(q.ctypes.data, b3.ctypes.data, p, tt, vec.ctypes.data)
+            vx, vy, vz = (int(x) for x in vec)
+            assert [vx, vy, vz] == [int(x) for x in rec[n][tt][:3]]
+            if vz != 1:
+                continue
+            u = vx - p if vx > half else vx
+            v = vy - p if vy > half else vy
+            au, hu, hv, bv = a * u, h * u, h * v, b * v
+            temp = au + hv + g
+            aa = c + u * temp + v * (bv + f)
+            gg = -(temp + au)
+            hh = f + hu + 2 * bv
+            bb, cc, ff = b, a, -h
+            if gg % p == 0:
+                continue                                   # rotated neighbor: the integer path
+            ginv = pow(gg % p, -1, p)
+            c1 = (-hh * ginv) % p
+            s1 = c1 - p if (hh > 0 and c1 >= p - half) else c1
+            c2 = (((-aa) % pp) * ginv) % pp
+            s2 = c2 - pp if c2 >= pp - (pp >> 1) else c2
+            temp1 = cc * s1
+            bb += s1 * (ff + temp1)
+            ff += 2 * temp1
+            hh1 = hh + s1 * gg
+            temp2 = cc * s2
+            num_a = aa + s2 * (gg + temp2)
+            num_h = hh1 + s2 * ff
+            assert num_a % pp == 0 and num_h % p == 0      # both divisions are exact (NeighborManager.h:338-341)
+            form = np.array([num_a // pp, bb, cc * pp, ff * p, gg + 2 * temp2, num_h // p], dtype=np.int64)
+            iso = np.array([u - s2, -s1 * p, -pp, v, p, 0, 1, 0, 0], dtype=np.int64)
+            lib.tbo_reduce(form.ctypes.data, iso.ctypes.data, 0)
+            assert np.array_equal(form, rec[n][tt][3:9]), (n, tt)
+            assert np.array_equal(iso, rec[n][tt][9:18]), (n, tt)
+            generic += 1
+    assert generic >= 0.9 * min(t.N, 6) * (p + 1)
