@@ -338,6 +338,7 @@ struct tb_genus {
     int64_t narrow_max_ratio = 32;      // narrow row output is attempted while (p+1)/N stays below this (TBIRCH_NARROW_MAX_RATIO)
     bool allow_fused = true;
     bool allow_acc = true;        // TBIRCH_ROWS_SORT: always the sorting row kernel (rows_kernel), never rows_acc_kernel
+    bool force_acc = false;       // TBIRCH_ROWS_ACC: rows_acc_kernel wherever its counters fit, whatever the row density
     bool force_checked = false;   // TBIRCH_FORCE_CHECKED: always run the checked C128 kernel in precise mode
     int last_int_mode = -1;       // tb_last_int_mode
     bool force_wide = false;      // TBIRCH_FORCE_WIDE: never run precise launches in the bounded 64-bit mode
@@ -588,6 +589,7 @@ extern "C" int tb_genus_create(const tb_genus_desc *d, tb_genus **out)
     g->force_checked = getenv("TBIRCH_FORCE_CHECKED") != nullptr;
     g->force_wide = getenv("TBIRCH_FORCE_WIDE") != nullptr;
     g->no_fp64_reduce = getenv("TBIRCH_NO_FP64_REDUCE") != nullptr;
+    g->force_acc = getenv("TBIRCH_ROWS_ACC") != nullptr;
     g->allow_narrow = getenv("TBIRCH_NO_NARROW_COPY") == nullptr;   // otherwise ReadbackPolicy decides per T_p,
     g->force_narrow = getenv("TBIRCH_FORCE_NARROW_COPY") != nullptr; // unless this pins the 3-byte format
     if (const char *e = getenv("TBIRCH_NARROW_MIN_NNZ")) g->narrow_min_nnz = std::max(1ll, atoll(e));
@@ -1056,7 +1058,11 @@ extern "C" int tb_hecke_compute_rows(tb_genus *g, uint64_t p, int precise, int64
     // rows_acc_kernel (accumulate with shared-memory atomics, no sort) when its state fits one SM and a class is
     // not expected to be hit anywhere near 256 times; it reports the rare overflow and the sorting kernel redoes the pass
     const size_t smem_acc = rows_acc_smem_bytes(N, P1);
-    bool use_acc = g->allow_acc && !R.scratch && smem_acc <= 216 * 1024 && (u64)P1 <= 48ull * (u64)N;
+    // ... and when the row is dense enough: the byte-counter kernel sweeps all N / 32 mask words twice per chunk of 8
+    // conductors, the sorting kernel only touches the p + 1 words, so below about N / 4 neighbors per row the sort wins
+    // (C2, N = 2016, 32 conductors, p = 101: 140 us against 315; C4, N = 10316, p = 9973: 2.96 ms against 2.25)
+    bool use_acc = g->allow_acc && !R.scratch && smem_acc <= 216 * 1024 && (u64)P1 <= 48ull * (u64)N &&
+                   (g->force_acc || 4ull * (u64)P1 >= (u64)N);
     // function attributes are per device (context): set them once on each device this process uses
     static std::atomic<uint64_t> attrs_mask(0);
     int attr_dev = 0;

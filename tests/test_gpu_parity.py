@@ -378,17 +378,20 @@ def test_narrow_readback_matches_plain(tables, monkeypatch, name, p, want_narrow
 @pytest.mark.parametrize("env", [dict(TBIRCH_TWO_PASS_ROWS="1"), dict(TBIRCH_TWO_PASS_ROWS="1", TBIRCH_NARROW_MIN_NNZ="1"),
                                  dict(TBIRCH_ROWS_SCRATCH="1"), dict(TBIRCH_ROWS_SCRATCH="1", TBIRCH_TWO_PASS_ROWS="1"),
                                  dict(TBIRCH_NARROW_MIN_NNZ="1", TBIRCH_NARROW_MAX_RATIO="100000"),
-                                 dict(TBIRCH_TWO_PASS_ROWS="1", TBIRCH_NARROW_MIN_NNZ="1", TBIRCH_NARROW_MAX_RATIO="100000")])
+                                 dict(TBIRCH_TWO_PASS_ROWS="1", TBIRCH_NARROW_MIN_NNZ="1", TBIRCH_NARROW_MAX_RATIO="100000"),
+                                 dict(TBIRCH_ROWS_ACC="1"), dict(TBIRCH_ROWS_SORT="1")])
 def test_row_kernel_variants_agree(tables, port_oracle, monkeypatch, env):
     """The row phase has a fused single-pass form and a count/scan/fill form, each with int32 or narrow
     output.  With the narrow attempt forced at p = 16381 >> N = 130 an entry exceeds 8 bits, so the fused form
     must redo the row pass in int32 and the two-pass form must pick int32 after its count pass.  All variants
     equal the oracle.  TBIRCH_ROWS_SCRATCH forces the form the kernel takes when a row's sort state exceeds
     one SM's shared memory (more than ~20000 classes at p > ~30000): the state in a global-memory slot per
-    CTA, CTAs walking the rows persistently."""
+    CTA, CTAs walking the rows persistently.  The single-pass form is the byte-counter kernel (rows_acc_kernel)
+    on dense rows and the sorting kernel (rows_kernel) on sparse ones; TBIRCH_ROWS_ACC / TBIRCH_ROWS_SORT take
+    each of them through all three primes."""
     from ternary_birch_b200 import Genus
     for k in ("TBIRCH_TWO_PASS_ROWS", "TBIRCH_NARROW_MIN_NNZ", "TBIRCH_NARROW_MAX_RATIO", "TBIRCH_NO_NARROW_COPY",
-              "TBIRCH_ROWS_SCRATCH"):
+              "TBIRCH_ROWS_SCRATCH", "TBIRCH_ROWS_ACC", "TBIRCH_ROWS_SORT"):
         monkeypatch.delenv(k, raising=False)
     monkeypatch.delenv("TBIRCH_FORCE_NARROW_COPY", raising=False)
     for k, v in env.items():
